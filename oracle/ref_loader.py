@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE ONLY -- import the UNMODIFIED reference under stub Blender modules.
+
+Works only where ``/root/reference`` exists (this container; NOT the GPU box).  Used by
+``oracle/gen_golden.py`` to produce ``tests/golden/*.npz`` and by the CPU tests that pin
+``oracle/icp_oracle.py`` against the live reference when it is present.
+
+Nothing from the reference is copied: its modules are executed from where they lie.
+The stubs exist because ``functions/general.py:26`` star-imports ``functions/common``,
+whose modules import ``bpy``/``bmesh``/``mathutils`` and read ``bpy.app.version`` at import
+time (functions/common/blender.py:24-30, wrappers.py:45), and ``operators/icp_align.py``
+imports ``bpy``, ``mathutils.Matrix`` and ``mathutils.bvhtree.BVHTree`` (:24-27).
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+import warnings
+
+from . import mathutils_shim as ms
+
+REFERENCE_ROOT = os.environ.get("ICP_REFERENCE_ROOT", "/root/reference")
+_PKG = "refpkg_object_alignment"
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "functions", "general.py"))
+
+
+class _Anything:
+    """Permissive stand-in for bpy.types classes / bpy.props factories."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return None
+
+    def __getattr__(self, name):
+        return _Anything()
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    return m
+
+
+def _install_stubs():
+    if "bpy" in sys.modules and getattr(sys.modules["bpy"], "_icp_stub", False):
+        return
+    bpy = _module("bpy", _icp_stub=True)
+    bpy.app = types.SimpleNamespace(version=(3, 2, 2), version_string="3.2.2")
+    bpy.context = types.SimpleNamespace(scene=types.SimpleNamespace(objects=[]))
+    bpy.data = types.SimpleNamespace()
+    bpy.ops = _Anything()
+    bpy.utils = _Anything()
+    bpy_types = _module("bpy.types")
+    for cls in ("Object", "Scene", "ViewLayer", "Operator", "Panel", "AddonPreferences",
+                "CollectionProperty", "Mesh", "Material", "Image", "Collection"):
+        setattr(bpy_types, cls, type(cls, (), {}))
+    bpy.types = bpy_types
+    bpy_props = _module("bpy.props")
+    for p in ("IntProperty", "BoolProperty", "FloatProperty", "EnumProperty", "StringProperty",
+              "FloatVectorProperty", "PointerProperty", "CollectionProperty",
+              "IntVectorProperty", "BoolVectorProperty"):
+        setattr(bpy_props, p, lambda *a, **k: None)
+    bpy.props = bpy_props
+    mathutils = _module("mathutils", Vector=ms.Vector, Matrix=ms.Matrix,
+                        Euler=type("Euler", (), {}), Color=type("Color", (), {}),
+                        Quaternion=ms.Quaternion)
+    bvhtree = _module("mathutils.bvhtree")
+    from .icp_oracle import NearestVertexBVH
+
+    bvhtree.BVHTree = NearestVertexBVH
+    mathutils.bvhtree = bvhtree
+    bpy_extras = _module("bpy_extras")
+    view3d_utils = _module("bpy_extras.view3d_utils")
+    for fn in ("location_3d_to_region_2d", "region_2d_to_vector_3d", "region_2d_to_origin_3d"):
+        setattr(view3d_utils, fn, lambda *a, **k: None)
+    bpy_extras.view3d_utils = view3d_utils
+    mods = {
+        "bpy": bpy, "bpy.types": bpy_types, "bpy.props": bpy_props,
+        "bmesh": _module("bmesh"), "bgl": _module("bgl"), "blf": _module("blf"),
+        "gpu": _module("gpu"),
+        "mathutils": mathutils, "mathutils.bvhtree": bvhtree,
+        "bpy_extras": bpy_extras, "bpy_extras.view3d_utils": view3d_utils,
+    }
+    for k, v in mods.items():
+        sys.modules.setdefault(k, v)
+
+
+def _synthetic_package(name, path):
+    """A package object whose __init__.py is NOT executed (so no registration side effects)."""
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg = types.ModuleType(name)
+    pkg.__path__ = [path]
+    pkg.__package__ = name
+    sys.modules[name] = pkg
+    return pkg
+
+
+def load_reference():
+    """Returns (general_module, icp_align_module) executed from /root/reference, unmodified."""
+    if not available():
+        raise FileNotFoundError(REFERENCE_ROOT)
+    _install_stubs()
+    _synthetic_package(_PKG, REFERENCE_ROOT)
+    _synthetic_package(_PKG + ".operators", os.path.join(REFERENCE_ROOT, "operators"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # general.py:106 has an invalid escape in a docstring
+        general = importlib.import_module(_PKG + ".functions.general")
+        icp_align = importlib.import_module(_PKG + ".operators.icp_align")
+    return general, icp_align
