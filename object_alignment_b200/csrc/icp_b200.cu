@@ -1,0 +1,1454 @@
+// icp_b200.cu -- libicp_b200.so: sm_100a kernels + the C ABI declared in include/icp_b200.h.
+//
+// One handle = one B200 + one stream.  An ICP iteration (the loop body of
+// OBJECT_OT_icp_align.execute, reference operators/icp_align.py:96-151) is this launch train,
+// with nothing crossing PCIe and no host synchronisation in between:
+//
+//   k_prepare_pose       imx1 = inv(mw_align), imx2 = inv(mw_base)              general.py:262-266
+//   k_transform_queries  q = imx2 @ (mx1 @ v.co) for the sampled vlist          general.py:274-275,287
+//   k_nn_bruteforce      nearest base vertex per query -> uint64 keys           general.py:297 (D2)
+//   [ncclAllReduce MIN over the keys when the base is sharded across ranks]
+//   [radix select of the reject_fraction percentile when enabled]               NEW
+//   k_filter_moments     world distance, thresh, targets, fp64 moment partials  general.py:299-328,160-181
+//   k_reduce_moments     fixed-order sum of the partials
+//   [ncclAllReduce SUM over 20 doubles when sharded]
+//   k_solve_update       Jacobi SVD -> R, scale, t -> M; matrix_world @= fp32(M); convergence ring
+//                                                   general.py:181-217, icp_align.py:116-149
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "../../include/icp_b200.h"
+#include "device_math.cuh"
+#include "nn_bruteforce.cuh"
+
+namespace icp {
+
+constexpr int MOM = 20;          // K, sum a'(3), sum b'(3), sum b' a'^T (9), sum|a'|^2, sum|b'|^2, sum d, sum d^2
+constexpr int MOM_THREADS = 256;
+
+struct DevState {
+    float mw_align[16];
+    float mw_base[16];
+    float imx1[16];
+    float imx2[16];
+    double M[16];
+    double ring[5];
+    double shift[3];             // a0: moments are accumulated about this point (cancellation guard)
+    int n_iter;
+    int converged;               // also used as the "stop" flag read by every kernel
+    int error;                   // icp_status raised on the device (too few pairs, singular)
+    int pad;
+    unsigned long long sel_prefix, sel_mask, sel_threshold;
+    long long sel_rank;
+    int sel_valid;
+    int pad2;
+};
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_prepare_pose(DevState* st)
+{
+    if (st->converged) return;
+    if (!s2_invert(st->mw_align, st->imx1) || !s2_invert(st->mw_base, st->imx2)) {
+        st->error = ICP_ERR_SINGULAR;
+        st->converged = 1;
+    }
+}
+
+// base upload: raw xyz -> tile-blocked SoA (+inf padded) and float4 AoS for gathers
+__global__ void k_build_base(const float* __restrict__ xyz, long long n, long long n_padded,
+                             float* __restrict__ tiles, float4* __restrict__ base4)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_padded) return;
+    const float inf = __int_as_float(0x7f800000);
+    float x = inf, y = inf, z = inf;
+    if (j < n) {
+        x = xyz[3 * j]; y = xyz[3 * j + 1]; z = xyz[3 * j + 2];
+        base4[j] = make_float4(x, y, z, 0.0f);
+    }
+    float* t = tiles + (j / NN_TILE) * (NN_TILE * 3) + (j % NN_TILE);
+    t[0] = x; t[NN_TILE] = y; t[2 * NN_TILE] = z;
+}
+
+// K1: sampled vertex -> base-local query (two S1 products), SoA out; keys reset to "none"
+__global__ void k_transform_queries(const DevState* __restrict__ st, const float* __restrict__ mov,
+                                    const int* __restrict__ vlist, int stride, long long n_q,
+                                    float* __restrict__ qx, float* __restrict__ qy,
+                                    float* __restrict__ qz, unsigned long long* __restrict__ keys)
+{
+    if (st->converged) return;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_q) return;
+    const long long vi = vlist ? (long long)vlist[p * stride] : p * stride;
+    const float ax = mov[3 * vi], ay = mov[3 * vi + 1], az = mov[3 * vi + 2];
+    float wx, wy, wz, x, y, z;
+    s1_matvec(st->mw_align, ax, ay, az, wx, wy, wz);
+    s1_matvec(st->imx2, wx, wy, wz, x, y, z);
+    qx[p] = x; qy[p] = y; qz[p] = z;
+    keys[p] = KEY_NONE;
+}
+
+// ---- percentile (reject_fraction) : exact radix select of the K-th smallest composite key
+//      composite(p) = d2_bits(p) << 32 | p          (NEW semantics)
+__global__ void k_select_init(DevState* st, long long rank, unsigned int* hist)
+{
+    const int t = threadIdx.x;
+    if (t < 256) hist[t] = 0;
+    if (t == 0) {
+        st->sel_prefix = 0; st->sel_mask = 0; st->sel_rank = rank; st->sel_threshold = 0;
+        st->sel_valid = rank >= 0 ? 1 : 0;
+    }
+}
+__global__ void k_select_hist(const DevState* __restrict__ st,
+                              const unsigned long long* __restrict__ keys, long long n, int byte,
+                              unsigned int* __restrict__ hist)
+{
+    if (st->converged) return;
+    __shared__ unsigned int sh[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = st->sel_prefix, mask = st->sel_mask;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = (keys[p] & 0xFFFFFFFF00000000ull) | (unsigned long long)p;
+        if ((c & mask) == prefix) atomicAdd(&sh[(c >> (8 * byte)) & 0xFF], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+__global__ void k_select_pick(DevState* st, int byte, unsigned int* hist)
+{
+    if (st->converged) return;
+    if (threadIdx.x == 0 && st->sel_valid) {
+        long long r = st->sel_rank;
+        int d = 0;
+        for (; d < 256; ++d) {
+            const long long c = hist[d];
+            if (r < c) break;
+            r -= c;
+        }
+        if (d == 256) { d = 255; st->sel_valid = 0; }
+        st->sel_rank = r;
+        st->sel_prefix |= (unsigned long long)d << (8 * byte);
+        st->sel_mask |= 0xFFull << (8 * byte);
+        if (byte == 0) st->sel_threshold = st->sel_prefix;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+}
+
+// ---- K3 + K4 : filter and fp64 moments ------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct PairEval {
+    bool keep;
+    float ax, ay, az, bx, by, bz;
+    double dist;
+};
+
+// everything the reference does for one vertex after find_nearest (general.py:299-306)
+__device__ __forceinline__ PairEval eval_pair(const DevState* __restrict__ st,
+                                              const float* __restrict__ mov,
+                                              const int* __restrict__ vlist, int stride,
+                                              const float* __restrict__ qx,
+                                              const float* __restrict__ qy,
+                                              const float* __restrict__ qz,
+                                              const unsigned long long* __restrict__ keys,
+                                              const float4* __restrict__ base4, long long base_off,
+                                              long long n_local, double thresh, int use_select,
+                                              long long p)
+{
+    PairEval e;
+    e.keep = false;
+    const unsigned long long key = keys[p];
+    if (key == KEY_NONE) return e;
+    const long long j = (long long)(uint32_t)(key & 0xFFFFFFFFull) - base_off;
+    if (j < 0 || j >= n_local) return e;                        // another rank owns this target
+    if (use_select) {
+        const unsigned long long c = (key & 0xFFFFFFFF00000000ull) | (unsigned long long)p;
+        if (!st->sel_valid || c > st->sel_threshold) return e;
+    }
+    const float4 co1 = base4[j];
+    float wqx, wqy, wqz, w1x, w1y, w1z;
+    s1_matvec(st->mw_base, qx[p], qy[p], qz[p], wqx, wqy, wqz);
+    s1_matvec(st->mw_base, co1.x, co1.y, co1.z, w1x, w1y, w1z);
+    e.dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+    if (!(e.dist < thresh)) return e;                            // strict, general.py:302
+    const long long vi = vlist ? (long long)vlist[p * stride] : p * stride;
+    e.ax = mov[3 * vi]; e.ay = mov[3 * vi + 1]; e.az = mov[3 * vi + 2];
+    s1_matvec(st->imx1, w1x, w1y, w1z, e.bx, e.by, e.bz);        // general.py:304
+    e.keep = true;
+    return e;
+}
+
+__global__ void __launch_bounds__(MOM_THREADS)
+k_filter_moments(const DevState* __restrict__ st, const float* __restrict__ mov,
+                 const int* __restrict__ vlist, int stride, long long n_q,
+                 const float* __restrict__ qx, const float* __restrict__ qy,
+                 const float* __restrict__ qz, const unsigned long long* __restrict__ keys,
+                 const float4* __restrict__ base4, long long base_off, long long n_local,
+                 double thresh, int use_select, double* __restrict__ partials)
+{
+    if (st->converged) return;
+    double acc[MOM];
+#pragma unroll
+    for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
+    const double s0 = st->shift[0], s1 = st->shift[1], s2 = st->shift[2];
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_q;
+         p += (long long)gridDim.x * blockDim.x) {
+        const PairEval e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off,
+                                     n_local, thresh, use_select, p);
+        if (!e.keep) continue;
+        const double a0 = (double)e.ax - s0, a1 = (double)e.ay - s1, a2 = (double)e.az - s2;
+        const double b0 = (double)e.bx - s0, b1 = (double)e.by - s1, b2 = (double)e.bz - s2;
+        acc[0] += 1.0;
+        acc[1] += a0; acc[2] += a1; acc[3] += a2;
+        acc[4] += b0; acc[5] += b1; acc[6] += b2;
+        acc[7] += b0 * a0; acc[8] += b0 * a1; acc[9] += b0 * a2;
+        acc[10] += b1 * a0; acc[11] += b1 * a1; acc[12] += b1 * a2;
+        acc[13] += b2 * a0; acc[14] += b2 * a1; acc[15] += b2 * a2;
+        acc[16] += a0 * a0 + a1 * a1 + a2 * a2;
+        acc[17] += b0 * b0 + b1 * b1 + b2 * b2;
+        acc[18] += e.dist;
+        acc[19] += e.dist * e.dist;
+    }
+    __shared__ double sh[MOM_THREADS / 32][MOM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < MOM; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) sh[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < MOM) {
+        double v = 0.0;
+        for (int w = 0; w < MOM_THREADS / 32; ++w) v += sh[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * MOM + threadIdx.x] = v;
+    }
+}
+
+// moments of explicit pair arrays (affine_matrix_from_points entry; v0, v1 are 3 x K row-major)
+__global__ void __launch_bounds__(MOM_THREADS)
+k_pairs_moments(const double* __restrict__ v0, const double* __restrict__ v1, long long K,
+                const DevState* __restrict__ st, double* __restrict__ partials)
+{
+    double acc[MOM];
+#pragma unroll
+    for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
+    const double s0 = st->shift[0], s1 = st->shift[1], s2 = st->shift[2];
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < K;
+         k += (long long)gridDim.x * blockDim.x) {
+        const double a0 = v0[k] - s0, a1 = v0[K + k] - s1, a2 = v0[2 * K + k] - s2;
+        const double b0 = v1[k] - s0, b1 = v1[K + k] - s1, b2 = v1[2 * K + k] - s2;
+        acc[0] += 1.0;
+        acc[1] += a0; acc[2] += a1; acc[3] += a2;
+        acc[4] += b0; acc[5] += b1; acc[6] += b2;
+        acc[7] += b0 * a0; acc[8] += b0 * a1; acc[9] += b0 * a2;
+        acc[10] += b1 * a0; acc[11] += b1 * a1; acc[12] += b1 * a2;
+        acc[13] += b2 * a0; acc[14] += b2 * a1; acc[15] += b2 * a2;
+        acc[16] += a0 * a0 + a1 * a1 + a2 * a2;
+        acc[17] += b0 * b0 + b1 * b1 + b2 * b2;
+    }
+    __shared__ double sh[MOM_THREADS / 32][MOM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < MOM; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) sh[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < MOM) {
+        double v = 0.0;
+        for (int w = 0; w < MOM_THREADS / 32; ++w) v += sh[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * MOM + threadIdx.x] = v;
+    }
+}
+
+// fixed-order sum of the per-CTA partials -> moments[MOM]   (one CTA of MOM warps)
+__global__ void k_reduce_moments(const DevState* __restrict__ st, const double* __restrict__ partials,
+                                 int n_partials, double* __restrict__ moments)
+{
+    if (st != nullptr && st->converged) return;
+    const int lane = threadIdx.x & 31, comp = threadIdx.x >> 5;
+    if (comp >= MOM) return;
+    double v = 0.0;
+    for (int i = lane; i < n_partials; i += 32) v += partials[(size_t)i * MOM + comp];
+    v = warp_sum(v);
+    if (lane == 0) moments[comp] = v;
+}
+
+// Kabsch/Umeyama step from the moments (general.py:160-217 for shear=False, usesvd=True)
+__device__ inline bool solve_from_moments(const double* mom, const double* shift, int scale_mode,
+                                          double* M /*4x4*/, double* mean_d, double* std_d)
+{
+    const double K = mom[0];
+    if (!(K >= 3.0)) return false;
+    double ca[3], cb[3];
+    for (int i = 0; i < 3; ++i) { ca[i] = mom[1 + i] / K; cb[i] = mom[4 + i] / K; }
+    double h[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) h[i * 3 + j] = mom[7 + i * 3 + j] - K * cb[i] * ca[j];
+    double rot[9];
+    rotation_from_covariance(h, rot);
+    if (scale_mode) {
+        const double va = mom[16] - K * (ca[0] * ca[0] + ca[1] * ca[1] + ca[2] * ca[2]);
+        const double vb = mom[17] - K * (cb[0] * cb[0] + cb[1] * cb[1] + cb[2] * cb[2]);
+        const double s = sqrt(vb / va);                          // general.py:208-212
+        for (int i = 0; i < 9; ++i) rot[i] *= s;
+    }
+    // un-shift the centroids, then t = cb - R ca                 (general.py:215-217)
+    for (int i = 0; i < 3; ++i) { ca[i] += shift[i]; cb[i] += shift[i]; }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) M[i * 4 + j] = rot[i * 3 + j];
+        M[i * 4 + 3] = cb[i] - (rot[i * 3] * ca[0] + rot[i * 3 + 1] * ca[1] + rot[i * 3 + 2] * ca[2]);
+    }
+    M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
+    const double m = mom[18] / K;
+    double var = mom[19] / K - m * m;
+    *mean_d = m;
+    *std_d = sqrt(var > 0 ? var : 0.0);
+    return true;
+}
+
+__device__ inline double rotation_angle_of(const float* nm)
+{
+    double r[9], tr = 0;
+    for (int j = 0; j < 3; ++j) {
+        double n = 0;
+        for (int i = 0; i < 3; ++i) n += (double)nm[i * 4 + j] * (double)nm[i * 4 + j];
+        n = sqrt(n);
+        if (n == 0) n = 1;
+        for (int i = 0; i < 3; ++i) r[i * 3 + j] = (double)nm[i * 4 + j] / n;
+    }
+    tr = r[0] + r[4] + r[8];
+    double c = (tr - 1.0) * 0.5;
+    c = c > 1 ? 1 : (c < -1 ? -1 : c);
+    return acos(c);
+}
+
+// K5: solve, pose update (icp_align.py:116-121), record, convergence ring (icp_align.py:136-142)
+__global__ void k_solve_update(DevState* st, const double* __restrict__ moments, int scale_mode,
+                               int use_target, double target_d, icp_iter_stats* __restrict__ stats,
+                               int stats_capacity)
+{
+    if (threadIdx.x != 0 || st->converged) return;
+    double M[16], mean_d, std_d;
+    if (!solve_from_moments(moments, st->shift, scale_mode, M, &mean_d, &std_d)) {
+        st->error = ICP_ERR_TOO_FEW_PAIRS;
+        st->converged = 1;
+        return;
+    }
+    float nm[16];
+    for (int i = 0; i < 16; ++i) { st->M[i] = M[i]; nm[i] = __double2float_rn(M[i]); }
+    float mw[16];
+    s3_matmul(st->mw_align, nm, mw);
+    for (int i = 0; i < 16; ++i) st->mw_align[i] = mw[i];
+    const double tlen = s5_length(nm[3], nm[7], nm[11]);
+    const int n = st->n_iter;
+    if (stats != nullptr && n < stats_capacity) {
+        icp_iter_stats& s = stats[n];
+        s.pairs = (int64_t)moments[0];
+        s.mean_dist = mean_d; s.std_dist = std_d; s.trans = tlen;
+        s.angle = rotation_angle_of(nm);
+        for (int i = 0; i < 16; ++i) s.M[i] = M[i];
+    }
+    if (use_target) {
+        st->ring[n % 5] = tlen;
+        bool all = true;
+        for (int i = 0; i < 5; ++i) all = all && (st->ring[i] < target_d);
+        if (all) st->converged = 1;
+    }
+    st->n_iter = n + 1;
+}
+
+// solve only (affine_matrix_from_points entry point): no pose update
+__global__ void k_solve_only(DevState* st, const double* __restrict__ moments, int scale_mode)
+{
+    if (threadIdx.x != 0) return;
+    double M[16], mean_d, std_d;
+    if (!solve_from_moments(moments, st->shift, scale_mode, M, &mean_d, &std_d)) {
+        st->error = ICP_ERR_TOO_FEW_PAIRS;
+        return;
+    }
+    for (int i = 0; i < 16; ++i) st->M[i] = M[i];
+}
+
+// ---- make_pairs emission: count, scan, scatter ------------------------------------------------
+constexpr int EMIT_THREADS = 256;
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+k_pairs_count(const DevState* __restrict__ st, const float* __restrict__ mov,
+              const int* __restrict__ vlist, int stride, long long n_q, const float* __restrict__ qx,
+              const float* __restrict__ qy, const float* __restrict__ qz,
+              const unsigned long long* __restrict__ keys, const float4* __restrict__ base4,
+              long long base_off, long long n_local, double thresh, int use_select,
+              unsigned char* __restrict__ flags, long long* __restrict__ block_counts)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (p < n_q) {
+        keep = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off, n_local, thresh,
+                         use_select, p).keep;
+        flags[p] = keep ? 1 : 0;
+    }
+    const int c = __syncthreads_count(keep ? 1 : 0);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+__global__ void k_scan_counts(long long* __restrict__ block_counts, int n_blocks, long long* total)
+{
+    // single thread: n_blocks <= a few 10k
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long run = 0;
+    for (int i = 0; i < n_blocks; ++i) { const long long c = block_counts[i]; block_counts[i] = run; run += c; }
+    *total = run;
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+k_pairs_emit(const DevState* __restrict__ st, const float* __restrict__ mov,
+             const int* __restrict__ vlist, int stride, long long n_q, const float* __restrict__ qx,
+             const float* __restrict__ qy, const float* __restrict__ qz,
+             const unsigned long long* __restrict__ keys, const float4* __restrict__ base4,
+             long long base_off, long long n_local, double thresh, int use_select,
+             const long long* __restrict__ block_offsets, long long K, double* __restrict__ A,
+             double* __restrict__ B, double* __restrict__ dist_out)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PairEval e;
+    e.keep = false;
+    if (p < n_q)
+        e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off, n_local, thresh,
+                      use_select, p);
+    __shared__ int warp_counts[EMIT_THREADS / 32];
+    const unsigned ballot = __ballot_sync(0xffffffffu, e.keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_counts[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_counts[w];
+    before += __popc(ballot & ((1u << lane) - 1u));
+    if (e.keep) {
+        const long long k = block_offsets[blockIdx.x] + before;
+        A[k] = e.ax; A[K + k] = e.ay; A[2 * K + k] = e.az;
+        B[k] = e.bx; B[K + k] = e.by; B[2 * K + k] = e.bz;
+        dist_out[k] = e.dist;
+    }
+}
+
+// mean / population std of the kept distances, two-pass like np.mean / np.std (general.py:324-325)
+__global__ void k_dist_stats(const double* __restrict__ dist, long long K, double* __restrict__ out)
+{
+    __shared__ double sh[32];
+    __shared__ double mean_s;
+    double s = 0;
+    for (long long i = threadIdx.x; i < K; i += blockDim.x) s += dist[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+        mean_s = t / (double)K;
+    }
+    __syncthreads();
+    const double m = mean_s;
+    double v = 0;
+    for (long long i = threadIdx.x; i < K; i += blockDim.x) { const double d = dist[i] - m; v += d * d; }
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+        out[0] = m;
+        out[1] = sqrt(t / (double)K);
+    }
+}
+
+__global__ void k_unpack_keys(const unsigned long long* __restrict__ keys, long long n,
+                              int* __restrict__ idx, float* __restrict__ d2)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned long long k = keys[p];
+    if (idx) idx[p] = (k == KEY_NONE) ? -1 : (int)(uint32_t)(k & 0xFFFFFFFFull);
+    if (d2) d2[p] = __uint_as_float((uint32_t)(k >> 32));
+}
+
+// ---- measurement helpers ----------------------------------------------------------------------
+__global__ void k_fma_peak(float* out, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+          a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+}
+__global__ void k_fma2_peak(float* out, int iters)
+{
+    uint64_t a0 = pk2(threadIdx.x * 1e-3f, 1.f), a1 = pk2(2.f, 3.f), a2 = pk2(4.f, 5.f),
+             a3 = pk2(6.f, 7.f), a4 = pk2(8.f, 9.f), a5 = pk2(1.5f, 2.5f), a6 = pk2(3.5f, 4.5f),
+             a7 = pk2(5.5f, 6.5f);
+    const uint64_t m = pk2(0.999f, 0.998f), c = pk2(1e-3f, 2e-3f);
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma2(a0, m, c); a1 = fma2(a1, m, c); a2 = fma2(a2, m, c); a3 = fma2(a3, m, c);
+        a4 = fma2(a4, m, c); a5 = fma2(a5, m, c); a6 = fma2(a6, m, c); a7 = fma2(a7, m, c);
+    }
+    float lo, hi, s = 0;
+    unpk2(a0, lo, hi); s += lo + hi; unpk2(a1, lo, hi); s += lo + hi;
+    unpk2(a2, lo, hi); s += lo + hi; unpk2(a3, lo, hi); s += lo + hi;
+    unpk2(a4, lo, hi); s += lo + hi; unpk2(a5, lo, hi); s += lo + hi;
+    unpk2(a6, lo, hi); s += lo + hi; unpk2(a7, lo, hi); s += lo + hi;
+    if (s == 12345.678f) out[0] = s;
+}
+__global__ void k_copy(const float4* __restrict__ src, float4* __restrict__ dst, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+}  // namespace icp
+
+// ==============================================================================================
+// host side
+// ==============================================================================================
+using namespace icp;
+
+namespace {
+
+char g_create_error[512] = "";
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(char* err, size_t n)
+    {
+        if (lib) return true;
+        // RTLD_NOLOAD first: reuse an NCCL already in the process (e.g. the one torch bundles)
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { snprintf(err, n, "dlopen(libnccl.so.2) failed: %s", dlerror()); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) {
+            snprintf(err, n, "libnccl is missing required symbols");
+            lib = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+struct EventPair { cudaEvent_t a, b; };
+
+}  // namespace
+
+struct icp_handle {
+    icp_params prm{};
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // base
+    float* d_base_tiles = nullptr;
+    float4* d_base4 = nullptr;
+    long long n_local = 0, n_global = 0, base_off = 0;
+    int n_tiles = 0;
+    bool have_base = false;
+    // moving
+    float* d_mov = nullptr;
+    long long mov_capacity = 0, n_vertices = 0;
+    int* d_vlist = nullptr;
+    long long vlist_capacity = 0, n_vlist = 0;
+    bool has_vlist = false, have_moving = false, have_matrices = false;
+    // queries
+    float* d_q = nullptr;                 // 3 planes of q_capacity
+    unsigned long long* d_keys = nullptr;
+    long long q_capacity = 0;
+    // reductions
+    double* d_partials = nullptr;
+    int partials_capacity = 0;
+    double* d_moments = nullptr;
+    unsigned int* d_hist = nullptr;
+    DevState* d_state = nullptr;
+    icp_iter_stats* d_stats = nullptr;
+    int stats_capacity = 0;
+    // make_pairs scratch
+    unsigned char* d_flags = nullptr;
+    long long* d_block_counts = nullptr;
+    long long* d_total = nullptr;
+    double* d_pairs = nullptr;            // A | B | dist
+    long long pairs_capacity = 0, flags_capacity = 0;
+    // solve_pairs scratch
+    double* d_v = nullptr;
+    long long v_capacity = 0;
+    // nccl
+    ncclComm_t comm = nullptr;
+    // measurement
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    bool profiling = false;
+    std::vector<EventPair> ev_pool[5];
+    size_t ev_used[5] = {0, 0, 0, 0, 0};
+    double ev_total_ms[5] = {0, 0, 0, 0, 0};
+    long long ev_launches[5] = {0, 0, 0, 0, 0};
+    long long launches = 0;
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    char err[512] = "";
+};
+
+namespace {
+
+int fail(icp_handle* h, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h ? h->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(h, _e == cudaErrorMemoryAllocation ? ICP_ERR_OOM : ICP_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,        \
+                        __LINE__);                                                               \
+    } while (0)
+
+#define NCCL_TRY(h, expr)                                                                        \
+    do {                                                                                         \
+        ncclResult_t _r = (expr);                                                                \
+        if (_r != ncclSuccess)                                                                   \
+            return fail(h, ICP_ERR_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(_r));     \
+    } while (0)
+
+template <typename T>
+int ensure(icp_handle* h, T*& ptr, long long& cap, long long need)
+{
+    if (need <= cap && ptr) return ICP_OK;
+    if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+    long long n = std::max<long long>(need, 1);
+    CUDA_TRY(h, cudaMalloc((void**)&ptr, (size_t)n * sizeof(T)));
+    cap = n;
+    return ICP_OK;
+}
+
+long long query_count(const icp_handle* h)
+{
+    const long long L = h->has_vlist ? h->n_vlist : h->n_vertices;
+    const long long s = h->prm.stride > 1 ? h->prm.stride : 1;
+    return (L + s - 1) / s;                       // len(vlist[0::s])
+}
+
+struct ProfScope {
+    icp_handle* h; int which; EventPair* ep = nullptr;
+    ProfScope(icp_handle* h_, int w) : h(h_), which(w)
+    {
+        if (!h->profiling) return;
+        auto& pool = h->ev_pool[which];
+        if (h->ev_used[which] == pool.size()) {
+            EventPair p;
+            cudaEventCreate(&p.a); cudaEventCreate(&p.b);
+            pool.push_back(p);
+        }
+        ep = &pool[h->ev_used[which]++];
+        cudaEventRecord(ep->a, h->stream);
+    }
+    ~ProfScope() { if (ep) cudaEventRecord(ep->b, h->stream); }
+};
+
+void collect_profile(icp_handle* h)
+{
+    for (int w = 0; w < 5; ++w) {
+        for (size_t i = 0; i < h->ev_used[w]; ++i) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->ev_pool[w][i].a, h->ev_pool[w][i].b) == cudaSuccess) {
+                h->ev_total_ms[w] += ms;
+                h->ev_launches[w] += 1;
+            }
+        }
+        h->ev_used[w] = 0;
+    }
+}
+
+// ---- K2 launch ---------------------------------------------------------------------------
+template <int R, int STAGES, bool PACKED>
+int launch_nn_t(icp_handle* h, long long n_q)
+{
+    auto kern = k_nn_bruteforce<R, STAGES, PACKED>;
+    const size_t smem = (size_t)STAGES * NN_TILE_BYTES + STAGES * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
+    // base ranges: enough CTAs for ~8 waves over the chip so the tail is small, but every CTA
+    // still streams >= 8 tiles so the TMA ring and the final index recovery are amortised
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)h->sm_count * occ;
+    long long want_y = (8 * slots + qb - 1) / qb;
+    long long max_y = std::max<long long>(1, h->n_tiles / 8);
+    long long gy = std::max<long long>(1, std::min(want_y, max_y));
+    int tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy);
+    gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    if (gy > 65535) { gy = 65535; tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy); gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta; }
+    dim3 grid((unsigned)qb, (unsigned)gy);
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_base_tiles, h->n_tiles, tiles_per_cta, qx, qy, qz,
+                                                n_q, h->d_keys, (uint32_t)h->base_off,
+                                                &h->d_state->converged);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+int launch_nn(icp_handle* h, long long n_q)
+{
+    if (n_q <= 0 || h->n_tiles <= 0) return ICP_OK;
+    ProfScope ps(h, 0);
+    switch (h->prm.nn_variant) {
+        case 1: return launch_nn_t<4, 4, false>(h, n_q);   // scalar pipe, 4 queries / thread
+        case 2: return launch_nn_t<4, 4, true>(h, n_q);    // packed f32x2
+        case 3: return launch_nn_t<8, 4, true>(h, n_q);
+        case 4: return launch_nn_t<2, 4, true>(h, n_q);
+        case 5: return launch_nn_t<8, 4, false>(h, n_q);
+        case 6: return launch_nn_t<6, 4, true>(h, n_q);
+        default: return launch_nn_t<4, 4, true>(h, n_q);
+    }
+}
+
+int moments_grid(const icp_handle* h, long long n)
+{
+    long long b = (n + MOM_THREADS - 1) / MOM_THREADS;
+    return (int)std::max<long long>(1, std::min<long long>(b, (long long)h->sm_count * 4));
+}
+
+int ensure_query_buffers(icp_handle* h, long long n_q)
+{
+    if (n_q > h->q_capacity || !h->d_q) {
+        if (h->d_q) cudaFree(h->d_q);
+        if (h->d_keys) cudaFree(h->d_keys);
+        h->d_q = nullptr; h->d_keys = nullptr; h->q_capacity = 0;
+        const long long cap = std::max<long long>(n_q, 1);
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_q, (size_t)cap * 3 * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_keys, (size_t)cap * sizeof(unsigned long long)));
+        h->q_capacity = cap;
+    }
+    const int g = moments_grid(h, n_q);
+    if (g > h->partials_capacity) {
+        if (h->d_partials) cudaFree(h->d_partials);
+        h->d_partials = nullptr;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_partials, (size_t)g * MOM * sizeof(double)));
+        h->partials_capacity = g;
+    }
+    return ICP_OK;
+}
+
+int check_ready(icp_handle* h)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    if (!h->have_base) return fail(h, ICP_ERR_STATE, "icp_set_base has not been called");
+    if (!h->have_moving) return fail(h, ICP_ERR_STATE, "icp_set_moving has not been called");
+    if (!h->have_matrices) return fail(h, ICP_ERR_STATE, "icp_set_matrices has not been called");
+    if (!(h->prm.thresh > 0))
+        return fail(h, ICP_ERR_BAD_ARG, "thresh must be > 0 (the reference's make_pairs returns None otherwise, general.py:277)");
+    return ICP_OK;
+}
+
+// transform + nearest neighbour (+ shard resolution + percentile select)
+int enqueue_nn(icp_handle* h, long long n_q)
+{
+    int rc = ensure_query_buffers(h, n_q);
+    if (rc) return rc;
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
+    {
+        ProfScope ps(h, 3);
+        k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
+        if (n_q > 0)
+            k_transform_queries<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(
+                h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q, qx, qy, qz,
+                h->d_keys);
+        h->launches += 2;
+    }
+    rc = launch_nn(h, n_q);
+    if (rc) return rc;
+    if (h->prm.world_size > 1 && n_q > 0) {
+        if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
+        ProfScope ps(h, 4);
+        NCCL_TRY(h, g_nccl.AllReduce(h->d_keys, h->d_keys, (size_t)n_q, ncclUint64, ncclMin, h->comm,
+                                     h->stream));
+    }
+    if (h->prm.reject_fraction > 0 && n_q > 0) {
+        ProfScope ps(h, 1);
+        const long long keep = n_q - (long long)std::floor(h->prm.reject_fraction * (double)n_q);
+        k_select_init<<<1, 256, 0, h->stream>>>(h->d_state, keep - 1, h->d_hist);
+        const int g = (int)std::min<long long>((n_q + 255) / 256, (long long)h->sm_count * 8);
+        for (int byte = 7; byte >= 0; --byte) {
+            k_select_hist<<<g, 256, 0, h->stream>>>(h->d_state, h->d_keys, n_q, byte, h->d_hist);
+            k_select_pick<<<1, 256, 0, h->stream>>>(h->d_state, byte, h->d_hist);
+        }
+        h->launches += 17;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+int enqueue_iteration(icp_handle* h, long long n_q)
+{
+    int rc = enqueue_nn(h, n_q);
+    if (rc) return rc;
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
+    const int g = moments_grid(h, n_q);
+    {
+        ProfScope ps(h, 1);
+        k_filter_moments<<<g, MOM_THREADS, 0, h->stream>>>(
+            h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q, qx, qy, qz,
+            h->d_keys, h->d_base4, h->base_off, h->n_local, h->prm.thresh,
+            h->prm.reject_fraction > 0 ? 1 : 0, h->d_partials);
+        k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
+        h->launches += 2;
+    }
+    if (h->prm.world_size > 1) {
+        ProfScope ps(h, 4);
+        NCCL_TRY(h, g_nccl.AllReduce(h->d_moments, h->d_moments, MOM, ncclDouble, ncclSum, h->comm,
+                                     h->stream));
+    }
+    {
+        ProfScope ps(h, 2);
+        k_solve_update<<<1, 32, 0, h->stream>>>(h->d_state, h->d_moments, h->prm.align_meth == 1,
+                                                h->prm.use_target, h->prm.target_d, h->d_stats,
+                                                h->stats_capacity);
+        h->launches += 1;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+int ensure_stats(icp_handle* h, int n)
+{
+    if (n <= h->stats_capacity) return ICP_OK;
+    // keep what is there (n_iter indexes into it)
+    icp_iter_stats* nw = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&nw, (size_t)n * sizeof(icp_iter_stats)));
+    CUDA_TRY(h, cudaMemsetAsync(nw, 0, (size_t)n * sizeof(icp_iter_stats), h->stream));
+    if (h->d_stats) {
+        CUDA_TRY(h, cudaMemcpyAsync(nw, h->d_stats, (size_t)h->stats_capacity * sizeof(icp_iter_stats),
+                                    cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_stats);
+    }
+    h->d_stats = nw;
+    h->stats_capacity = n;
+    return ICP_OK;
+}
+
+int read_state(icp_handle* h, DevState* out)
+{
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ICP_OK;
+}
+
+int device_error(icp_handle* h, const DevState& st)
+{
+    if (st.error == ICP_ERR_TOO_FEW_PAIRS)
+        return fail(h, ICP_ERR_TOO_FEW_PAIRS, "input arrays are of wrong shape or type");
+    if (st.error == ICP_ERR_SINGULAR)
+        return fail(h, ICP_ERR_SINGULAR, "Matrix.invert(ed): matrix does not have an inverse");
+    if (st.error) return fail(h, st.error, "device-side error %d", st.error);
+    return ICP_OK;
+}
+
+int clear_device_error(icp_handle* h)
+{
+    // error + its stop flag are cleared so the handle stays usable after a failed call
+    DevState st;
+    int rc = read_state(h, &st);
+    if (rc) return rc;
+    if (st.error) {
+        st.error = 0;
+        st.converged = 0;
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_state, &st, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return ICP_OK;
+}
+
+}  // namespace
+
+// ==============================================================================================
+// C ABI
+// ==============================================================================================
+extern "C" {
+
+int icp_version(void) { return ICP_B200_VERSION; }
+
+const char* icp_last_error(const icp_handle* h) { return h ? h->err : g_create_error; }
+
+int icp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -ICP_ERR_CUDA; }
+    return n;
+}
+
+int icp_create(const icp_params* p, icp_handle** out)
+{
+    if (!p || !out) return fail(nullptr, ICP_ERR_BAD_ARG, "icp_create: null argument");
+    if (p->struct_size != (int32_t)sizeof(icp_params))
+        return fail(nullptr, ICP_ERR_BAD_ARG, "icp_create: struct_size %d != %zu", p->struct_size, sizeof(icp_params));
+    if (p->world_size < 1 || p->rank < 0 || p->rank >= p->world_size)
+        return fail(nullptr, ICP_ERR_BAD_ARG, "icp_create: bad rank/world_size");
+    *out = nullptr;
+    icp_handle* h = new (std::nothrow) icp_handle();
+    if (!h) return fail(nullptr, ICP_ERR_OOM, "icp_create: out of host memory");
+    h->prm = *p;
+#define CREATE_TRY(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            fail(nullptr, ICP_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));          \
+            delete h;                                                                             \
+            return ICP_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(p->device));
+    cudaDeviceProp prop;
+    CREATE_TRY(cudaGetDeviceProperties(&prop, p->device));
+    if (prop.major != 10) {
+        fail(nullptr, ICP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+             p->device, prop.major, prop.minor);
+        delete h;
+        return ICP_ERR_CUDA;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreate(&h->ev0));
+    CREATE_TRY(cudaEventCreate(&h->ev1));
+    CREATE_TRY(cudaMalloc((void**)&h->d_state, sizeof(DevState)));
+    CREATE_TRY(cudaMemset(h->d_state, 0, sizeof(DevState)));
+    CREATE_TRY(cudaMalloc((void**)&h->d_moments, MOM * sizeof(double)));
+    CREATE_TRY(cudaMalloc((void**)&h->d_hist, 256 * sizeof(unsigned int)));
+    CREATE_TRY(cudaMalloc((void**)&h->d_total, sizeof(long long)));
+#undef CREATE_TRY
+    *out = h;
+    int rc = icp_reset_convergence(h);
+    if (rc) { snprintf(g_create_error, 512, "%s", h->err); icp_destroy(h); *out = nullptr; return rc; }
+    return ICP_OK;
+}
+
+int icp_destroy(icp_handle* h)
+{
+    if (!h) return ICP_OK;
+    cudaSetDevice(h->prm.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
+                    h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int w = 0; w < 5; ++w)
+        for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ICP_OK;
+}
+
+int icp_set_params(icp_handle* h, const icp_params* p)
+{
+    if (!h || !p) return ICP_ERR_BAD_ARG;
+    if (p->struct_size != (int32_t)sizeof(icp_params)) return fail(h, ICP_ERR_BAD_ARG, "bad struct_size");
+    if (p->device != h->prm.device || p->rank != h->prm.rank || p->world_size != h->prm.world_size)
+        return fail(h, ICP_ERR_BAD_ARG, "device / rank / world_size cannot change after icp_create");
+    h->prm = *p;
+    return ICP_OK;
+}
+
+int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t global_offset, int64_t n_global)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    if (n_local < 0 || global_offset < 0 || n_global < n_local || (n_local > 0 && !xyz))
+        return fail(h, ICP_ERR_BAD_ARG, "icp_set_base: bad sizes");
+    if (n_global > 0xFFFFFFFELL) return fail(h, ICP_ERR_BAD_ARG, "icp_set_base: more than 2^32-2 base vertices");
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    if (h->d_base_tiles) { cudaFree(h->d_base_tiles); h->d_base_tiles = nullptr; }
+    if (h->d_base4) { cudaFree(h->d_base4); h->d_base4 = nullptr; }
+    h->n_tiles = (int)((n_local + NN_TILE - 1) / NN_TILE);
+    const long long n_pad = (long long)h->n_tiles * NN_TILE;
+    h->n_local = n_local; h->n_global = n_global; h->base_off = global_offset;
+    if (n_local > 0) {
+        float* d_raw = nullptr;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_base_tiles, (size_t)n_pad * 3 * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_base4, (size_t)n_local * sizeof(float4)));
+        CUDA_TRY(h, cudaMalloc((void**)&d_raw, (size_t)n_local * 3 * sizeof(float)));
+        CUDA_TRY(h, cudaMemcpyAsync(d_raw, xyz, (size_t)n_local * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        k_build_base<<<(unsigned)((n_pad + 255) / 256), 256, 0, h->stream>>>(d_raw, n_local, n_pad, h->d_base_tiles, h->d_base4);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(d_raw);
+    }
+    h->have_base = true;
+    return ICP_OK;
+}
+
+int icp_set_moving(icp_handle* h, const float* xyz, int64_t n_vertices, const int32_t* vlist, int64_t n_vlist)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    if (n_vertices < 0 || (n_vertices > 0 && !xyz) || n_vlist < 0 || (vlist == nullptr && n_vlist != 0))
+        return fail(h, ICP_ERR_BAD_ARG, "icp_set_moving: bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    int rc = ensure(h, h->d_mov, h->mov_capacity, n_vertices * 3);
+    if (rc) return rc;
+    if (n_vertices > 0)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_mov, xyz, (size_t)n_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->n_vertices = n_vertices;
+    h->has_vlist = vlist != nullptr;
+    h->n_vlist = n_vlist;
+    double shift[3] = {0, 0, 0};
+    if (vlist) {
+        for (int64_t i = 0; i < n_vlist; ++i)
+            if (vlist[i] < 0 || vlist[i] >= n_vertices)
+                return fail(h, ICP_ERR_BAD_ARG, "icp_set_moving: vlist[%lld] = %d out of range", (long long)i, vlist[i]);
+        rc = ensure(h, h->d_vlist, h->vlist_capacity, n_vlist);
+        if (rc) return rc;
+        if (n_vlist > 0) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_vlist, vlist, (size_t)n_vlist * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            for (int k = 0; k < 3; ++k) shift[k] = xyz[3 * (int64_t)vlist[0] + k];
+        }
+    } else if (n_vertices > 0) {
+        for (int k = 0; k < 3; ++k) shift[k] = xyz[k];
+    }
+    CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, shift), shift, sizeof(shift), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_moving = true;
+    return ICP_OK;
+}
+
+int icp_set_matrices(icp_handle* h, const float mw_align[16], const float mw_base[16])
+{
+    if (!h || !mw_align || !mw_base) return ICP_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    float both[32];
+    memcpy(both, mw_align, 64);
+    memcpy(both + 16, mw_base, 64);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_state, both, sizeof(both), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_matrices = true;
+    return ICP_OK;
+}
+
+int icp_comm_unique_id(void* id128)
+{
+    if (!id128) return ICP_ERR_BAD_ARG;
+    if (!g_nccl.load(g_create_error, sizeof(g_create_error))) return ICP_ERR_NCCL;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, ICP_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    memcpy(id128, &id, 128);
+    return ICP_OK;
+}
+
+int icp_comm_init(icp_handle* h, const void* id128)
+{
+    if (!h || !id128) return ICP_ERR_BAD_ARG;
+    if (h->prm.world_size == 1) return ICP_OK;
+    if (!g_nccl.load(h->err, sizeof(h->err))) return ICP_ERR_NCCL;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCCL_TRY(h, g_nccl.CommInitRank(&h->comm, h->prm.world_size, id, h->prm.rank));
+    return ICP_OK;
+}
+
+int icp_query_count(const icp_handle* h, int64_t* n)
+{
+    if (!h || !n) return ICP_ERR_BAD_ARG;
+    *n = query_count(h);
+    return ICP_OK;
+}
+
+int icp_nn(icp_handle* h, int32_t* idx, float* d2)
+{
+    int rc = check_ready(h);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    const long long n_q = query_count(h);
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    rc = enqueue_nn(h, n_q);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    if (n_q > 0 && (idx || d2)) {
+        int* d_idx = nullptr; float* d_d2 = nullptr;
+        if (idx) CUDA_TRY(h, cudaMalloc((void**)&d_idx, (size_t)n_q * sizeof(int)));
+        if (d2) CUDA_TRY(h, cudaMalloc((void**)&d_d2, (size_t)n_q * sizeof(float)));
+        k_unpack_keys<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_keys, n_q, d_idx, d_d2);
+        h->launches++;
+        if (idx) CUDA_TRY(h, cudaMemcpyAsync(idx, d_idx, (size_t)n_q * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (d2) CUDA_TRY(h, cudaMemcpyAsync(d2, d_d2, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (d_idx) cudaFree(d_idx);
+        if (d_d2) cudaFree(d_d2);
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_ms = ms;
+    collect_profile(h);
+    DevState st;
+    rc = read_state(h, &st);
+    if (rc) return rc;
+    rc = device_error(h, st);
+    if (rc) { clear_device_error(h); return rc; }
+    return ICP_OK;
+}
+
+int icp_make_pairs(icp_handle* h, int calc_stats, double* A, double* B, int64_t capacity,
+                   int64_t* pairs_out, double d_stats[2])
+{
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (h->prm.world_size > 1)
+        return fail(h, ICP_ERR_STATE, "icp_make_pairs materialises pairs on one GPU; use icp_step/icp_run with sharded bases");
+    if (!pairs_out) return fail(h, ICP_ERR_BAD_ARG, "icp_make_pairs: pairs_out is null");
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    const long long n_q = query_count(h);
+    rc = enqueue_nn(h, n_q);
+    if (rc) return rc;
+    const int nb = (int)std::max<long long>(1, (n_q + EMIT_THREADS - 1) / EMIT_THREADS);
+    if (n_q > h->flags_capacity || !h->d_flags) {
+        if (h->d_flags) cudaFree(h->d_flags);
+        if (h->d_block_counts) cudaFree(h->d_block_counts);
+        h->d_flags = nullptr; h->d_block_counts = nullptr;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_flags, (size_t)std::max<long long>(n_q, 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_block_counts, (size_t)nb * sizeof(long long)));
+        h->flags_capacity = std::max<long long>(n_q, 1);
+    }
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
+    const int* vl = h->has_vlist ? h->d_vlist : nullptr;
+    const int use_sel = h->prm.reject_fraction > 0 ? 1 : 0;
+    k_pairs_count<<<nb, EMIT_THREADS, 0, h->stream>>>(h->d_state, h->d_mov, vl, stride, n_q, qx, qy, qz,
+                                                      h->d_keys, h->d_base4, h->base_off, h->n_local,
+                                                      h->prm.thresh, use_sel, h->d_flags, h->d_block_counts);
+    k_scan_counts<<<1, 32, 0, h->stream>>>(h->d_block_counts, nb, h->d_total);
+    h->launches += 2;
+    long long K = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&K, h->d_total, sizeof(K), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    DevState st;
+    rc = read_state(h, &st);
+    if (rc) return rc;
+    rc = device_error(h, st);
+    if (rc) { clear_device_error(h); return rc; }
+    *pairs_out = K;
+    if (!A && !B) return ICP_OK;
+    if (!A || !B) return fail(h, ICP_ERR_BAD_ARG, "icp_make_pairs: A and B must both be given");
+    if (capacity < K) return fail(h, ICP_ERR_BAD_ARG, "icp_make_pairs: capacity %lld < %lld pairs", (long long)capacity, K);
+    if (K > 0) {
+        rc = ensure(h, h->d_pairs, h->pairs_capacity, 7 * K + 2);
+        if (rc) return rc;
+        double* dA = h->d_pairs; double* dB = dA + 3 * K; double* dD = dB + 3 * K; double* dS = dD + K;
+        k_pairs_emit<<<nb, EMIT_THREADS, 0, h->stream>>>(h->d_state, h->d_mov, vl, stride, n_q, qx, qy, qz,
+                                                         h->d_keys, h->d_base4, h->base_off, h->n_local,
+                                                         h->prm.thresh, use_sel, h->d_block_counts, K, dA, dB, dD);
+        h->launches++;
+        // A, B have row stride K on the device; the caller's have row stride `capacity`
+        CUDA_TRY(h, cudaMemcpy2DAsync(A, (size_t)capacity * sizeof(double), dA, (size_t)K * sizeof(double),
+                                      (size_t)K * sizeof(double), 3, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpy2DAsync(B, (size_t)capacity * sizeof(double), dB, (size_t)K * sizeof(double),
+                                      (size_t)K * sizeof(double), 3, cudaMemcpyDeviceToHost, h->stream));
+        if (calc_stats && d_stats) {
+            k_dist_stats<<<1, 1024, 0, h->stream>>>(dD, K, dS);
+            h->launches++;
+            CUDA_TRY(h, cudaMemcpyAsync(d_stats, dS, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    } else if (calc_stats && d_stats) {
+        d_stats[0] = d_stats[1] = NAN;                 // np.mean([]) -> nan
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+int icp_solve_pairs(icp_handle* h, const double* v0, const double* v1, int64_t K, int scale, double M_out[16])
+{
+    if (!h || !v0 || !v1 || !M_out || K < 0) return h ? fail(h, ICP_ERR_BAD_ARG, "icp_solve_pairs: bad argument") : ICP_ERR_BAD_ARG;
+    if (K < 3) return fail(h, ICP_ERR_TOO_FEW_PAIRS, "input arrays are of wrong shape or type");
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    int rc = ensure(h, h->d_v, h->v_capacity, 6 * K);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_v, v0, (size_t)3 * K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_v + 3 * K, v1, (size_t)3 * K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // moments about the first source point; the handle's own shift is restored afterwards
+    DevState st;
+    rc = read_state(h, &st);
+    if (rc) return rc;
+    const double keep_shift[3] = {st.shift[0], st.shift[1], st.shift[2]};
+    const double shift[3] = {v0[0], v0[K], v0[2 * K]};
+    CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, shift), shift, sizeof(shift), cudaMemcpyHostToDevice, h->stream));
+    const int g = moments_grid(h, K);
+    if (g > h->partials_capacity) {
+        if (h->d_partials) cudaFree(h->d_partials);
+        h->d_partials = nullptr;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_partials, (size_t)g * MOM * sizeof(double)));
+        h->partials_capacity = g;
+    }
+    k_pairs_moments<<<g, MOM_THREADS, 0, h->stream>>>(h->d_v, h->d_v + 3 * K, K, h->d_state, h->d_partials);
+    k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(nullptr, h->d_partials, g, h->d_moments);
+    k_solve_only<<<1, 32, 0, h->stream>>>(h->d_state, h->d_moments, scale ? 1 : 0);
+    h->launches += 3;
+    CUDA_TRY(h, cudaGetLastError());
+    rc = read_state(h, &st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, shift), keep_shift, sizeof(keep_shift), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    rc = device_error(h, st);
+    if (rc) { clear_device_error(h); return rc; }
+    memcpy(M_out, st.M, sizeof(st.M));
+    return ICP_OK;
+}
+
+int icp_run(icp_handle* h, int32_t max_iters, int32_t* iters_done, int32_t* converged, icp_iter_stats* per_iter)
+{
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (max_iters < 0) return fail(h, ICP_ERR_BAD_ARG, "icp_run: max_iters < 0");
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    DevState st0;
+    rc = read_state(h, &st0);
+    if (rc) return rc;
+    rc = ensure_stats(h, st0.n_iter + max_iters);
+    if (rc) return rc;
+    const long long n_q = query_count(h);
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    for (int it = 0; it < max_iters; ++it) {
+        rc = enqueue_iteration(h, n_q);
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    DevState st;
+    rc = read_state(h, &st);
+    if (rc) return rc;
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_ms = ms;
+    collect_profile(h);
+    const int done = st.n_iter - st0.n_iter;
+    if (iters_done) *iters_done = done;
+    if (converged) *converged = (st.converged && !st.error) ? 1 : 0;
+    if (per_iter && done > 0) {
+        CUDA_TRY(h, cudaMemcpy(per_iter, h->d_stats + st0.n_iter, (size_t)done * sizeof(icp_iter_stats), cudaMemcpyDeviceToHost));
+    }
+    rc = device_error(h, st);
+    if (rc) { clear_device_error(h); return rc; }
+    return ICP_OK;
+}
+
+int icp_step(icp_handle* h, double M_out[16], icp_iter_stats* stats)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    icp_iter_stats s;
+    memset(&s, 0, sizeof(s));
+    int done = 0, conv = 0;
+    // a single step ignores an earlier "converged" latch: the caller decides when to stop
+    DevState st;
+    int rc = check_ready(h);
+    if (rc) return rc;
+    rc = read_state(h, &st);
+    if (rc) return rc;
+    if (st.converged) {
+        int zero = 0;
+        CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, converged), &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = icp_run(h, 1, &done, &conv, &s);
+    if (rc) return rc;
+    if (done != 1) return fail(h, ICP_ERR_STATE, "icp_step: iteration did not execute");
+    if (M_out) memcpy(M_out, s.M, sizeof(s.M));
+    if (stats) *stats = s;
+    return ICP_OK;
+}
+
+int icp_reset_convergence(icp_handle* h)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    DevState st;
+    int rc = read_state(h, &st);
+    if (rc) return rc;
+    for (int i = 0; i < 5; ++i) st.ring[i] = h->prm.target_d * 2;   // icp_align.py:93
+    st.n_iter = 0; st.converged = 0; st.error = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ICP_OK;
+}
+
+int icp_get_matrix_world(icp_handle* h, float out[16])
+{
+    if (!h || !out) return ICP_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    DevState st;
+    int rc = read_state(h, &st);
+    if (rc) return rc;
+    memcpy(out, st.mw_align, 64);
+    return ICP_OK;
+}
+
+int icp_last_elapsed_ms(const icp_handle* h, double* ms)
+{
+    if (!h || !ms) return ICP_ERR_BAD_ARG;
+    *ms = h->last_ms;
+    return ICP_OK;
+}
+
+int icp_set_profiling(icp_handle* h, int enabled)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    h->profiling = enabled != 0;
+    for (int w = 0; w < 5; ++w) { h->ev_total_ms[w] = 0; h->ev_launches[w] = 0; h->ev_used[w] = 0; }
+    return ICP_OK;
+}
+
+int icp_kernel_time_ms(const icp_handle* h, int which, double* total_ms, int64_t* launches)
+{
+    if (!h || which < 0 || which > 4) return ICP_ERR_BAD_ARG;
+    if (total_ms) *total_ms = h->ev_total_ms[which];
+    if (launches) *launches = h->ev_launches[which];
+    return ICP_OK;
+}
+
+int icp_launch_count(const icp_handle* h, int64_t* launches)
+{
+    if (!h || !launches) return ICP_ERR_BAD_ARG;
+    *launches = h->launches;
+    return ICP_OK;
+}
+
+int icp_synchronize(icp_handle* h)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ICP_OK;
+}
+
+static int ensure_scratch(icp_handle* h, size_t bytes)
+{
+    if (h->scratch_bytes >= bytes) return ICP_OK;
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    h->d_scratch = nullptr; h->scratch_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->d_scratch, bytes));
+    h->scratch_bytes = bytes;
+    return ICP_OK;
+}
+
+int icp_measure_fp32_peak(icp_handle* h, double* tflops)
+{
+    if (!h || !tflops) return ICP_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    int rc = ensure_scratch(h, 1 << 20);
+    if (rc) return rc;
+    const int iters = 1 << 15, blocks = h->sm_count * 8, threads = 256;
+    double best = 0;
+    for (int variant = 0; variant < 2; ++variant) {
+        for (int rep = 0; rep < 4; ++rep) {
+            CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+            if (variant == 0) k_fma_peak<<<blocks, threads, 0, h->stream>>>((float*)h->d_scratch, iters);
+            else k_fma2_peak<<<blocks, threads, 0, h->stream>>>((float*)h->d_scratch, iters);
+            CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            const double fl = 2.0 * (variant ? 2.0 : 1.0) * 8.0 * iters * (double)blocks * threads;
+            if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        }
+    }
+    h->launches += 8;
+    *tflops = best;
+    return ICP_OK;
+}
+
+int icp_measure_copy_bandwidth(icp_handle* h, double* gbs)
+{
+    if (!h || !gbs) return ICP_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    const size_t half = (size_t)1 << 30;      // 1 GiB read + 1 GiB write
+    int rc = ensure_scratch(h, 2 * half);
+    if (rc) return rc;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        k_copy<<<h->sm_count * 16, 512, 0, h->stream>>>((const float4*)h->d_scratch, (float4*)((char*)h->d_scratch + half), (long long)(half / 16));
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        if (rep > 0) best = std::max(best, 2.0 * half / (ms * 1e-3) / 1e9);
+    }
+    h->launches += 5;
+    *gbs = best;
+    return ICP_OK;
+}
+
+int icp_flush_l2(icp_handle* h)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    const size_t bytes = (size_t)256 << 20;   // 2x the 126 MB L2
+    int rc = ensure_scratch(h, bytes);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_scratch, 0, bytes, h->stream));
+    return ICP_OK;
+}
+
+int icp_alloc_pinned(size_t bytes, void** out)
+{
+    if (!out) return ICP_ERR_BAD_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, ICP_ERR_OOM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return ICP_OK;
+}
+
+int icp_free_pinned(void* ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+    return ICP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+"""OBJECT_OT_icp_align -- the reference's operator surface over the GPU engine.
+
+Same class attributes and methods as reference operators/icp_align.py:32-161
+(``bl_idname``/``bl_label``/``bl_options``, ``poll``, ``execute``); registrable by the same
+``bpy.utils.register_class`` loop (reference __init__.py:43-53).  Outside Blender (tests, the
+GPU box) ``bpy`` is absent and ``Operator`` is a plain base class.
+
+execute() keeps the reference's observable behaviour -- same vertex-group rule, same
+parameters, same per-iteration pose update and convergence test -- but runs the whole
+``while n < iters and not converged`` loop (icp_align.py:96-151) on the GPU through
+``icp_run`` and writes ``matrix_world`` back once.  The depsgraph refresh the reference does
+every iteration (icp_align.py:132-133) happens once at the end.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import _native as N
+from .engine import IcpError, stride_from_sample_fraction
+from .functions import VertexNN, array_to_matrix_like, extract_coords, matrix_to_array
+from .preferences import get_addon_preferences
+
+try:  # inside Blender
+    import bpy  # type: ignore
+    from bpy.types import Operator  # type: ignore
+except ImportError:  # anywhere else
+    bpy = None
+
+    class Operator:  # minimal stand-in so the class body below is importable
+        def report(self, level, message):
+            print("%s: %s" % ("/".join(sorted(level)), message))
+
+
+def build_vlist(align_obj) -> np.ndarray:
+    """Vertex-group rule of the reference (operators/icp_align.py:56-80) -> ascending int32.
+
+    'icp_include' wins over 'icp_exclude' (the ``elif`` at :67); include keeps members with
+    weight > 0.9 (:64); exclude keeps non-members (:71) and members with weight < 0.1 (:75).
+    """
+    verts = align_obj.data.vertices
+    lookup = {g.name: g.index for g in align_obj.vertex_groups}
+    n = len(verts)
+    if "icp_include" in align_obj.vertex_groups:
+        gi = lookup["icp_include"]
+        keep = np.zeros(n, dtype=bool)
+        for v in verts:
+            for g in v.groups:
+                if g.group == gi and g.weight > 0.9:
+                    keep[v.index] = True
+        return np.nonzero(keep)[0].astype(np.int32)
+    if "icp_exclude" in align_obj.vertex_groups:
+        gi = lookup["icp_exclude"]
+        keep = np.zeros(n, dtype=bool)
+        for v in verts:
+            member = False
+            for g in v.groups:
+                if g.group == gi:
+                    member = True
+                    if g.weight < 0.1:
+                        keep[v.index] = True
+            if not member:
+                keep[v.index] = True
+        return np.nonzero(keep)[0].astype(np.int32)
+    return np.arange(n, dtype=np.int32)
+
+
+def build_vlist_from_arrays(n_verts, groups) -> np.ndarray:
+    """Same rule on bulk arrays: groups = {name: (member_mask bool[n], weight float32[n])}."""
+    groups = groups or {}
+    if "icp_include" in groups:
+        mask, w = groups["icp_include"]
+        keep = np.asarray(mask, bool) & (np.asarray(w, np.float32).astype(np.float64) > 0.9)
+    elif "icp_exclude" in groups:
+        mask, w = groups["icp_exclude"]
+        mask = np.asarray(mask, bool)
+        keep = (~mask) | (np.asarray(w, np.float32).astype(np.float64) < 0.1)
+    else:
+        keep = np.ones(int(n_verts), dtype=bool)
+    return np.nonzero(keep)[0].astype(np.int32)
+
+
+def _apply_to_m_objects(context, new_mats):
+    """take_m_with (icp_align.py:123-127): post-multiply every scene object named 'm_*'."""
+    scene_objects = None
+    if bpy is not None:
+        scene_objects = bpy.context.scene.objects
+    elif hasattr(context, "scene"):
+        scene_objects = context.scene.objects
+    if not scene_objects:
+        return
+    for obj in scene_objects:
+        if obj.name[:2] == "m_":
+            for nm in new_mats:
+                obj.matrix_world = obj.matrix_world @ array_to_matrix_like(nm, obj.matrix_world)
+            obj.update_tag()
+
+
+class OBJECT_OT_icp_align(Operator):
+    """Uses ICP alignment to iteratively align two objects (GPU engine)"""
+    bl_idname = "object.align_icp"
+    bl_label = "ICP Align"
+    bl_options = {'REGISTER', 'UNDO'}
+
+    # engine knobs that have no counterpart in the reference's preferences
+    device = 0
+    reject_fraction = 0.0
+
+    @classmethod
+    def poll(cls, context):
+        condition_1 = len(context.selected_objects) == 2
+        condition_2 = context.object.type == 'MESH'
+        return condition_1 and condition_2
+
+    def execute(self, context):
+        settings = get_addon_preferences()
+        start = time.time()
+        align_obj = context.object
+        base_obj = [obj for obj in context.selected_objects if obj != align_obj][0]
+        align_obj.rotation_mode = 'QUATERNION'
+
+        vlist = build_vlist(align_obj)
+        factor = stride_from_sample_fraction(settings.sample_fraction)   # ZeroDivisionError at 0
+        thresh = settings.min_start
+        if not thresh > 0:
+            # the reference's make_pairs returns None here and the unpack at icp_align.py:101 raises
+            raise TypeError("cannot unpack non-iterable NoneType object")
+
+        base_nn = VertexNN.FromObject(
+            base_obj, context.evaluated_depsgraph_get(), device=self.device, thresh=thresh,
+            target_d=settings.target_d, use_target=settings.use_target,
+            align_meth=settings.align_meth, stride=factor, reject_fraction=self.reject_fraction)
+        try:
+            eng = base_nn.engine
+            eng.set_moving(extract_coords(align_obj), vlist)
+            eng.set_matrices(matrix_to_array(align_obj.matrix_world),
+                             matrix_to_array(base_obj.matrix_world))
+            try:
+                done, converged, recs = eng.run(settings.icp_iterations)
+            except IcpError as e:
+                if e.code == N.ICP_ERR_TOO_FEW_PAIRS:
+                    raise ValueError("input arrays are of wrong shape or type") from None
+                raise
+            align_obj.matrix_world = array_to_matrix_like(eng.matrix_world(), align_obj.matrix_world)
+        finally:
+            base_nn.close()
+        if settings.take_m_with:
+            _apply_to_m_objects(context, [r.M.astype(np.float32) for r in recs])
+        align_obj.update_tag()
+        context.view_layer.update()
+
+        self.iterations = done
+        self.converged = converged
+        self.records = recs
+        if settings.use_target and recs:
+            last = recs[-1]
+            print('Converged in %s iterations' % done if converged else 'Maxed out iterations')
+            print('Final Translation: %f ' % last.trans)
+            print('Final Avg Dist: %f' % last.mean_dist)
+            print('Final St Dev %f' % last.std_dist)
+            print('Avg last 5 rotation angle: %f' % np.mean([r.angle for r in recs[-5:]]))
+        print('Aligned obj in %f sec' % (time.time() - start))
+        return {'FINISHED'}

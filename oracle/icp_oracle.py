@@ -260,7 +260,9 @@ def length3_vec(d: np.ndarray) -> np.ndarray:
 
 def percentile_keep_port(dist: np.ndarray, reject_fraction: float) -> np.ndarray:
     """NEW semantics: keep the K = L - floor(reject_fraction * L) queries with the
-    smallest (dist, query_position) lexicographic key.  Returns a bool mask over positions."""
+    smallest (d, query_position) lexicographic key, where d is the fp32 base-local squared
+    distance S4 carried in the NN key (it is the one quantity every rank holds for every query
+    once the shards are resolved).  Returns a bool mask over positions."""
     n = dist.shape[0]
     k = n - int(math.floor(float(reject_fraction) * n))
     order = np.lexsort((np.arange(n), dist))
@@ -302,7 +304,7 @@ def make_pairs_vec(coords, vlist, mw_align, mw_base, base, thresh, sample=0, cal
     dist = length3_vec((wq - w1).astype(f32))                         # general.py:299
     keep = dist < float(thresh)                                       # general.py:302 (strict)
     if reject_fraction and reject_fraction > 0:
-        keep &= percentile_keep_port(dist, reject_fraction)
+        keep &= percentile_keep_port(d2, reject_fraction)
     b = matvec43_vec(imx1, w1)                                        # general.py:304
     A = np.ascontiguousarray(a[keep].astype(f64).T)                   # general.py:313-321
     B = np.ascontiguousarray(b[keep].astype(f64).T)

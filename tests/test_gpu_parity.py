@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) and the reference-shaped
+Python surface, against the CPU oracle and the golden files of the unmodified reference.
+
+Bar: indices / kept sets / A / B bit-exact; fp64 solver outputs within 1e-9; the composed
+pose (rotation and translation after all iterations) within 1e-5 of the reference
+(BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+import object_alignment_b200 as oab
+from object_alignment_b200 import meshgen
+from object_alignment_b200.engine import IcpEngine, IcpError
+from oracle import icp_oracle as orc
+from oracle import mathutils_shim as ms
+from tests.golden_util import GOLDEN, Golden, scenario_names
+
+pytestmark = pytest.mark.gpu
+
+NN_VARIANTS = [0, 1, 2, 3, 4, 5, 6]
+
+
+def _rand_cloud(n, seed, scale=1.0):
+    return (np.random.default_rng(seed).standard_normal((n, 3)) * scale).astype(np.float32)
+
+
+# ------------------------------------------------------------------ K2: nearest vertex
+@pytest.mark.parametrize("variant", NN_VARIANTS)
+def test_nn_bit_exact_small(variant):
+    base = _rand_cloud(5000, 1)
+    base[1234] = base[77]                      # exact tie -> lowest index must win
+    base[4999] = base[0]
+    mov = np.concatenate([base[[77, 0]], _rand_cloud(3001, 2)])
+    with IcpEngine(nn_variant=variant) as e:
+        e.set_base(base)
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+    oi, od = orc.nn_bruteforce(mov, base)
+    assert idx[0] == 77 and idx[1] == 0 and d2[0] == 0.0
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+
+
+@pytest.mark.parametrize("n_base,n_mov", [(1, 1), (1, 300), (15, 7), (16, 257), (1023, 1),
+                                          (1024, 1024), (1025, 1025), (4097, 2049),
+                                          (9000, 12345)])
+def test_nn_ragged_sizes(n_base, n_mov):
+    base = _rand_cloud(n_base, 10 + n_base)
+    mov = _rand_cloud(n_mov, 20 + n_mov)
+    with IcpEngine() as e:
+        e.set_base(base)
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+    oi, od = orc.nn_bruteforce(mov, base)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+
+
+def test_nn_empty_inputs():
+    with IcpEngine() as e:
+        e.set_base(np.zeros((0, 3), np.float32))
+        e.set_moving(_rand_cloud(10, 1))
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+        assert (idx == -1).all()
+        e.set_base(_rand_cloud(10, 2))
+        e.set_moving(np.zeros((0, 3), np.float32))
+        idx, d2 = e.nn()
+        assert idx.shape == (0,)
+        with pytest.raises(IcpError) as ei:
+            e.step()                                  # no pairs -> the solver's ValueError
+        assert ei.value.code == 2
+
+
+def test_nn_vlist_stride_and_matrices():
+    base = _rand_cloud(3000, 5)
+    mov = _rand_cloud(2500, 6)
+    mw_a = meshgen.rigid_matrix(13.0, (0.2, -0.1, 0.05))
+    mw_b = meshgen.rigid_matrix(-21.0, (0.0, 0.3, -0.2), axis=(0.3, 0.1, -1.0)).astype(np.float64)
+    mw_b[:3, :3] = mw_b[:3, :3] @ np.diag([1.2, 0.9, 1.05])
+    mw_b = mw_b.astype(np.float32)
+    vlist = np.sort(np.random.default_rng(7).choice(2500, 1700, replace=False)).astype(np.int32)
+    for stride in (0, 1, 2, 3, 7):
+        with IcpEngine(stride=stride) as e:
+            e.set_base(base)
+            e.set_moving(mov, vlist)
+            e.set_matrices(mw_a, mw_b)
+            idx, d2 = e.nn()
+        res = orc.make_pairs_vec(mov, vlist, mw_a, mw_b, base, 1e9, stride, return_all=True)
+        assert idx.shape == res["idx"].shape
+        assert np.array_equal(idx, res["idx"])
+        assert np.array_equal(d2.view(np.uint32), res["d2"].view(np.uint32))
+
+
+def test_nn_100k_vs_100k_c2():
+    cfg = meshgen.config_cloud(100_000, 100_000, 100, 101)
+    with IcpEngine() as e:
+        e.set_base(cfg["base"])
+        e.set_moving(cfg["moving"])
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+    oi, od = orc.nn_bruteforce(cfg["moving"], cfg["base"])
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+
+
+def test_nn_full_size_properties_1m():
+    """C3 size (1M x 1M): size-independent properties + an oracle spot check."""
+    cfg = meshgen.config_cloud(1_000_000, 1_000_000, 200, 201)
+    base, mov = cfg["base"], cfg["moving"]
+    with IcpEngine() as e:
+        e.set_base(base)
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+        idx_again, d2_again = e.nn()                          # idempotent / deterministic
+        assert np.array_equal(idx, idx_again) and np.array_equal(d2, d2_again)
+        # a base vertex used as a query finds itself (or an identical earlier vertex) at d2 == 0
+        e.set_moving(base[::97])
+        sidx, sd2 = e.nn()
+        assert (sd2 == 0).all()
+        assert np.array_equal(base[sidx], base[::97]) and (sidx <= np.arange(0, 1_000_000, 97)).all()
+    assert idx.min() >= 0 and idx.max() < 1_000_000
+    # reported distance is the S4 metric of the reported pair
+    assert np.array_equal(orc._d2_spec_numpy_exact(mov, base[idx]).view(np.uint32), d2.view(np.uint32))
+    # spot check 3000 queries against the CPU brute force
+    sel = np.random.default_rng(0).choice(1_000_000, 3000, replace=False)
+    oi, od = orc.nn_bruteforce(mov[sel], base)
+    assert np.array_equal(idx[sel], oi) and np.array_equal(d2[sel], od)
+    # sharding property: min over per-shard keys == unsharded keys
+    keys = []
+    with IcpEngine() as e:
+        e.set_moving(mov[:50_000])
+        e.set_matrices(np.eye(4), np.eye(4))
+        for lo, hi in ((0, 300_000), (300_000, 650_001), (650_001, 1_000_000)):
+            e.set_base(base[lo:hi], lo, 1_000_000)
+            i, d = e.nn()
+            keys.append(orc.pack_key(d, i))
+    assert np.array_equal(np.minimum.reduce(keys), orc.pack_key(d2[:50_000], idx[:50_000]))
+
+
+# ------------------------------------------------------------------ make_pairs / solver API
+def _objects(g):
+    align = ms.Object("align", g.moving, g.mw_align, g.groups)
+    base = ms.Object("base", g.base, g.mw_base)
+    return align, base
+
+
+@pytest.mark.parametrize("name", ["c1_worldmats", "c1_tight_thresh", "cloud_2k_3k", "c1_exclude"])
+def test_make_pairs_bit_exact(name):
+    g = Golden(name)
+    align, base = _objects(g)
+    vlist = oab.build_vlist(align)
+    assert np.array_equal(vlist, g.vlist)
+    nn = oab.VertexNN.FromObject(base, None)
+    try:
+        for thresh, sample, stats in ((g.prefs["min_start"], 1, True), (0.08, 2, True), (0.3, 3, False)):
+            A, B, ds = oab.make_pairs(align, base, nn, vlist, thresh, sample, calc_stats=stats)
+            oA, oB, ods = orc.make_pairs_vec(g.moving, vlist, g.mw_align, g.mw_base, g.base, thresh,
+                                             sample, calc_stats=stats)
+            assert A.shape == oA.shape and A.dtype == np.float64
+            assert np.array_equal(A, oA) and np.array_equal(B, oB)
+            if stats:
+                np.testing.assert_allclose(ds, ods, rtol=1e-12)
+            else:
+                assert ds is None
+        assert oab.make_pairs(align, base, nn, vlist, 0.0) is None           # general.py:277
+        assert oab.make_pairs(align, base, nn, vlist, -1.0) is None
+    finally:
+        nn.close()
+
+
+def test_affine_matrix_from_points_kat_and_errors():
+    z = np.load(GOLDEN + "/solver_kat.npz")
+    for tag, scale in (("rigid", False), ("sim", True), ("refl", False)):
+        M = oab.affine_matrix_from_points(z[tag + "_v0"], z[tag + "_v1"], shear=False, scale=scale,
+                                          usesvd=True)
+        np.testing.assert_allclose(M, z[tag + "_M"], rtol=0, atol=1e-9)
+    # far-from-origin data: the shifted moments must not cancel
+    rng = np.random.default_rng(5)
+    v0 = rng.standard_normal((3, 5000)) + np.array([[1e4], [-2e4], [3e4]])
+    R = meshgen.rotation_about_axis(17.0)
+    v1 = R @ v0 + np.array([[5.0], [6.0], [7.0]])
+    M = oab.affine_matrix_from_points(v0, v1, shear=False, scale=False, usesvd=True)
+    np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(v0, v1), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(M[:3, :3], R, atol=1e-9)
+    # planar (rank-2) and exactly 3 points
+    v0 = rng.standard_normal((3, 3))
+    v1 = R @ v0 + 1.0
+    M = oab.affine_matrix_from_points(v0, v1, shear=False, scale=False, usesvd=True)
+    np.testing.assert_allclose(M[:3, :3] @ v0 + M[:3, 3:4], v1, atol=1e-9)
+    with pytest.raises(ValueError, match="wrong shape or type"):
+        oab.affine_matrix_from_points(np.zeros((3, 2)), np.zeros((3, 2)), shear=False)
+    with pytest.raises(ValueError):
+        oab.affine_matrix_from_points(np.zeros((3, 5)), np.zeros((3, 4)), shear=False)
+    with pytest.raises(NotImplementedError):
+        oab.affine_matrix_from_points(np.zeros((3, 5)), np.zeros((3, 5)))    # shear=True default
+
+
+# ------------------------------------------------------------------ the operator, end to end
+@pytest.mark.parametrize("name", scenario_names())
+def test_operator_execute_matches_reference_golden(name):
+    g = Golden(name)
+    align, base = _objects(g)
+    oab.set_addon_preferences(oab.IcpPreferences(**g.prefs))
+    ctx = ms.Context(align, [align, base])
+    op = oab.OBJECT_OT_icp_align()
+    assert op.poll(ctx)
+    assert op.execute(ctx) == {"FINISHED"}
+    assert op.iterations == g.iterations
+    assert op.converged == g.converged
+    assert align.rotation_mode == "QUATERNION"
+    assert [r.pairs for r in op.records] == g.K.tolist()
+    for it, r in enumerate(op.records):
+        np.testing.assert_allclose(r.M, g.M[it], rtol=0, atol=1e-5)
+        if g.prefs["use_target"]:
+            np.testing.assert_allclose([r.mean_dist, r.std_dist], g.d_stats[it], rtol=1e-4)
+    np.testing.assert_allclose(align.matrix_world.a, g.matrix_world, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["c1_fixed20", "c1_worldmats", "c1_scale", "cloud_2k_3k"])
+def test_stepwise_parity_against_oracle(name):
+    """Every iteration is checked against the oracle started from the engine's OWN current pose,
+    so the comparison stays exact (indices, K) however many iterations are composed."""
+    g = Golden(name)
+    p = g.prefs
+    vlist = orc.build_vlist_port(g.moving.shape[0], g.groups)
+    stride = orc.stride_factor_port(p["sample_fraction"])
+    with IcpEngine(thresh=p["min_start"], target_d=p["target_d"], use_target=p["use_target"],
+                   align_meth=p["align_meth"], stride=stride) as e:
+        e.set_base(g.base)
+        e.set_moving(g.moving, vlist)
+        e.set_matrices(g.mw_align, g.mw_base)
+        for it in range(min(8, g.iterations)):
+            mw = e.matrix_world()
+            res = orc.make_pairs_vec(g.moving, vlist, mw, g.mw_base, g.base, p["min_start"], stride,
+                                     calc_stats=True, return_all=True)
+            idx, d2 = e.nn()
+            assert np.array_equal(idx, res["idx"])
+            assert np.array_equal(d2.view(np.uint32), res["d2"].view(np.uint32))
+            M, st = e.step()
+            assert st.pairs == int(res["keep"].sum())
+            Mo = orc.affine_matrix_from_points_port(res["A"], res["B"], scale=(p["align_meth"] == "1"))
+            np.testing.assert_allclose(M, Mo, rtol=0, atol=1e-10)
+            np.testing.assert_allclose([st.mean_dist, st.std_dist], res["d_stats"], rtol=1e-9)
+            np.testing.assert_allclose(st.trans, ms.length3(Mo.astype(np.float32)[:3, 3]), rtol=1e-6)
+            np.testing.assert_allclose(st.angle, orc.rotation_angle(Mo.astype(np.float32)), atol=1e-6)
+            # pose update: matrix_world @ fp32(M) with rule S3, bit-exact given the engine's M
+            np.testing.assert_array_equal(e.matrix_world(), ms.matmul44(mw, M.astype(np.float32)))
+
+
+def test_reference_shaped_loop_with_icp_step():
+    """The reference's own loop shape (icp_align.py:96-151), one fused call per iteration."""
+    g = Golden("c1_fixed20")
+    align, base = _objects(g)
+    vlist = oab.build_vlist(align)
+    nn = oab.VertexNN.FromObject(base, None)
+    try:
+        idx, dist = oab.calc_target(align, base, nn, vlist, 1)
+        assert np.array_equal(idx, g.idx[0])
+        for n in range(g.iterations):
+            M, st = oab.icp_step(align, base, nn, vlist, 0.5, 1, calc_stats=False)
+            np.testing.assert_allclose(M, g.M[n], atol=1e-5)
+        np.testing.assert_allclose(align.matrix_world.a, g.matrix_world, atol=1e-5)
+        with pytest.raises(TypeError):
+            oab.icp_step(align, base, nn, vlist, 0.0)
+        with pytest.raises(ValueError, match="wrong shape or type"):
+            oab.icp_step(align, base, nn, vlist, 1e-9)          # nothing survives the threshold
+        # the handle stays usable after the error
+        M, st = oab.icp_step(align, base, nn, vlist, 0.5, 1)
+        assert st.pairs == 1002
+    finally:
+        nn.close()
+
+
+# ------------------------------------------------------------------ percentile rejection (new)
+@pytest.mark.parametrize("rf", [0.25, 0.5, 0.013])
+def test_reject_fraction_matches_definition(rf):
+    cfg = meshgen.config_cloud(20_000, 30_000, 11, 12)
+    mov = cfg["moving"].copy()
+    rng = np.random.default_rng(13)
+    out = rng.choice(20_000, 5000, replace=False)
+    mov[out] = (rng.random((5000, 3)).astype(np.float32) - 0.5) * 6
+    mov[7] = mov[3]                                   # equal d2 at different positions
+    with IcpEngine(thresh=1e9, reject_fraction=rf, use_target=True) as e:
+        e.set_base(cfg["base"])
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        A, B, ds = e.make_pairs(calc_stats=True)
+        M, st = e.step()
+    res = orc.make_pairs_vec(mov, np.arange(20_000), np.eye(4), np.eye(4), cfg["base"], 1e9, 1,
+                             calc_stats=True, reject_fraction=rf, return_all=True)
+    assert A.shape[1] == 20_000 - int(np.floor(rf * 20_000)) == int(res["keep"].sum())
+    assert np.array_equal(A, res["A"]) and np.array_equal(B, res["B"])
+    np.testing.assert_allclose(ds, res["d_stats"], rtol=1e-12)
+    assert st.pairs == A.shape[1]
+    np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(res["A"], res["B"]), atol=1e-10)
+
+
+# ------------------------------------------------------------------ errors and misc
+def test_error_behaviour():
+    with IcpEngine() as e:
+        with pytest.raises(IcpError) as ei:
+            e.nn()
+        assert ei.value.code == 6                                 # ICP_ERR_STATE
+        e.set_base(_rand_cloud(100, 1))
+        e.set_moving(_rand_cloud(50, 2))
+        sing = np.eye(4, dtype=np.float32)
+        sing[2, 2] = 0.0
+        e.set_matrices(sing, np.eye(4))
+        with pytest.raises(IcpError) as ei:
+            e.step()
+        assert ei.value.code == 7                                 # Matrix.inverted() raises
+        e.set_matrices(np.eye(4), np.eye(4))
+        e.update_params(thresh=0.0)
+        with pytest.raises(IcpError) as ei:
+            e.step()
+        assert ei.value.code == 1
+        e.update_params(thresh=10.0)
+        M, st = e.step()
+        assert st.pairs == 50
+        with pytest.raises(IcpError):
+            e.set_moving(_rand_cloud(5, 1), np.array([0, 7], np.int32))   # vlist out of range
+    with pytest.raises(ZeroDivisionError):
+        oab.stride_from_sample_fraction(0)
+
+
+def test_run_is_deterministic_and_device_resident():
+    cfg = meshgen.config_cloud(30_000, 40_000, 31, 32)
+    outs = []
+    for _ in range(2):
+        with IcpEngine(thresh=0.5, use_target=False) as e:
+            e.set_base(cfg["base"])
+            e.set_moving(cfg["moving"])
+            e.set_matrices(np.eye(4), np.eye(4))
+            done, conv, recs = e.run(6)
+            assert done == 6 and not conv
+            outs.append((e.matrix_world(), [r.M for r in recs]))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, b)
+    # the pose converges towards the inverse of the 5 degree / (0.02,-0.01,0.03) offset
+    res = orc.icp_execute_port(cfg["moving"], np.arange(30_000), np.eye(4), np.eye(4), cfg["base"],
+                               thresh=0.5, sample_fraction=1.0, iters=6, use_target=False, nn="kdtree")
+    np.testing.assert_allclose(outs[0][0], res["matrix_world"], atol=1e-5)
