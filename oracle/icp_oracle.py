@@ -183,7 +183,7 @@ class NearestVertexBVH:
         self.log = []
         self.mode = mode
         self._tree = None
-        if mode == "kdtree" or (mode == "auto" and self.base.shape[0] > 4096):
+        if mode in ("kdtree", "kdtree_fast") or (mode == "auto" and self.base.shape[0] > 4096):
             from scipy.spatial import cKDTree
 
             self._tree = cKDTree(self.base.astype(f64))
@@ -196,6 +196,11 @@ class NearestVertexBVH:
         return cls(buf.reshape(-1, 3), mode=mode)
 
     def find_nearest(self, co):
+        if self.mode == "kdtree_fast":
+            # timing-only provider (bench.py cpu_baseline): one fp64 k=1 lookup, the cheapest
+            # stand-in for Blender's C BVH; no S4 re-check, so near-ties may differ from S4
+            d, j = self._tree.query(co.v)
+            return (ms.Vector(self.base[j]), None, j, d)
         q = np.array([co[0], co[1], co[2]], dtype=f32).reshape(1, 3)
         if self.base.shape[0] == 0:
             return (None, None, None, None)

@@ -51,15 +51,14 @@ def _f(x):
 
 
 def matvec43(m: np.ndarray, v) -> np.ndarray:
-    """S1 on raw arrays: m is (4,4) float32, v is 3 floats; returns (3,) float32."""
-    v4 = (f32(v[0]), f32(v[1]), f32(v[2]), f32(1.0))
-    out = np.empty(3, dtype=f32)
-    for r in range(3):
-        acc = f64(0.0)
-        for c in range(4):
-            acc = acc + f64(f32(m[r, c] * v4[c]))
-        out[r] = f32(acc)
-    return out
+    """S1 on raw arrays: m is (4,4) float32, v is 3 floats; returns (3,) float32.
+
+    Vectorised over the three rows, but the order of operations per row is exactly
+    ((p0 + p1) + p2) + p3 with float products and double accumulation."""
+    v4 = np.empty(4, dtype=f32)
+    v4[0], v4[1], v4[2], v4[3] = v[0], v[1], v[2], 1.0
+    p = (m[:3] * v4).astype(f64)          # float32 products, then widened (exact)
+    return (((p[:, 0] + p[:, 1]) + p[:, 2]) + p[:, 3]).astype(f32)
 
 
 def matmul44(a: np.ndarray, b: np.ndarray) -> np.ndarray:
@@ -129,10 +128,9 @@ def invert44(m_rowmajor: np.ndarray) -> np.ndarray:
 
 def length3(v) -> float:
     """S5: sqrt of the double sum of float squares, accumulated z, y, x."""
-    acc = f64(0.0)
-    for i in (2, 1, 0):
-        acc = acc + f64(f32(f32(v[i]) * f32(v[i])))
-    return math.sqrt(float(acc))
+    v = np.asarray(v, dtype=f32)
+    p = (v * v).astype(f64)
+    return math.sqrt(float((p[2] + p[1]) + p[0]))
 
 
 # --------------------------------------------------------------------------- types
