@@ -41,7 +41,8 @@ typedef enum icp_status {
 
 typedef enum icp_nn_mode {
     ICP_NN_BRUTEFORCE = 0, /* O(M N) tiled min-search, the north-star path (general.py:297, D2) */
-    ICP_NN_GRID = 1        /* uniform-grid exact search; bit-identical results */
+    ICP_NN_BVH = 1         /* exact search through an implicit BVH over Morton-sorted base vertices
+                              (the "KD-tree equivalent"); bit-identical results */
 } icp_nn_mode;
 
 /* Parameter block; mirrors ObjectAlignmentPreferences (lib/preferences.py:31-72) as read by
@@ -157,6 +158,10 @@ int  icp_measure_fp32_peak(icp_handle *h, double *tflops);
 int  icp_measure_copy_bandwidth(icp_handle *h, double *gbs);
 /* Overwrite a > L2-sized scratch buffer (flushes L2 between timed iterations). */
 int  icp_flush_l2(icp_handle *h);
+
+/* Debug counters of the BVH search (only counted when nn_variant == 99):
+ * out = {inner-node visits, leaf visits, stack pushes, queries}. */
+int  icp_debug_counters(icp_handle *h, uint64_t out[4], int reset);
 
 /* ---- pinned host staging buffers (so uploads run at full PCIe rate) ----------------------- */
 int  icp_alloc_pinned(size_t bytes, void **out);

@@ -21,7 +21,7 @@ ICP_ERR_STATE = 6
 ICP_ERR_SINGULAR = 7
 
 NN_BRUTEFORCE = 0
-NN_GRID = 1
+NN_BVH = 1
 
 
 class IcpParams(C.Structure):
@@ -90,6 +90,7 @@ SIGNATURES = {
     "icp_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "icp_measure_copy_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "icp_flush_l2": (C.c_int, [C.c_void_p]),
+    "icp_debug_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "icp_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "icp_free_pinned": (C.c_int, [C.c_void_p]),
 }

@@ -29,6 +29,9 @@
 #include "../../include/icp_b200.h"
 #include "device_math.cuh"
 #include "nn_bruteforce.cuh"
+#include "nn_bvh.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 namespace icp {
 
@@ -81,22 +84,93 @@ __global__ void k_build_base(const float* __restrict__ xyz, long long n, long lo
     t[0] = x; t[NN_TILE] = y; t[2 * NN_TILE] = z;
 }
 
-// K1: sampled vertex -> base-local query (two S1 products), SoA out; keys reset to "none"
+// K1: sampled vertex -> base-local query (two S1 products), SoA out, one query per SLOT.
+// slot_pos (nullable = identity) maps a slot to its query position: slots are the Morton order
+// of the moving vertices, so that neighbouring threads of the tree search walk the same nodes.
+// Keys are reset to "none" -- or, with `warm`, to the previous iteration's winner re-evaluated
+// under the new pose: a real base vertex, hence a valid candidate and a tight initial bound.
 __global__ void k_transform_queries(const DevState* __restrict__ st, const float* __restrict__ mov,
                                     const int* __restrict__ vlist, int stride, long long n_q,
+                                    const uint32_t* __restrict__ slot_pos,
                                     float* __restrict__ qx, float* __restrict__ qy,
-                                    float* __restrict__ qz, unsigned long long* __restrict__ keys)
+                                    float* __restrict__ qz, unsigned long long* __restrict__ keys,
+                                    int warm, const float4* __restrict__ base4, long long base_off,
+                                    long long n_local)
 {
     if (st->converged) return;
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_q) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_q) return;
+    const long long p = slot_pos ? (long long)slot_pos[t] : t;
     const long long vi = vlist ? (long long)vlist[p * stride] : p * stride;
     const float ax = mov[3 * vi], ay = mov[3 * vi + 1], az = mov[3 * vi + 2];
     float wx, wy, wz, x, y, z;
     s1_matvec(st->mw_align, ax, ay, az, wx, wy, wz);
     s1_matvec(st->imx2, wx, wy, wz, x, y, z);
-    qx[p] = x; qy[p] = y; qz[p] = z;
-    keys[p] = KEY_NONE;
+    qx[t] = x; qy[t] = y; qz[t] = z;
+    unsigned long long key = KEY_NONE;
+    if (warm) {
+        const unsigned long long old = keys[t];
+        const long long j = (long long)(uint32_t)(old & 0xFFFFFFFFull) - base_off;
+        if (old != KEY_NONE && j >= 0 && j < n_local) {
+            const float4 b = base4[j];
+            const float d = s4_d2(x, y, z, b.x, b.y, b.z);
+            if (d < __int_as_float(0x7f800000))
+                key = ((unsigned long long)__float_as_uint(d) << 32) | (old & 0xFFFFFFFFull);
+        }
+    }
+    keys[t] = key;
+}
+
+// Morton code of every sampled moving vertex (align-local space; a rigid pose keeps the order useful)
+__global__ void k_query_bbox_partial(const float* __restrict__ mov, const int* __restrict__ vlist, int stride,
+                                     long long n_q, float* __restrict__ part)
+{
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_q;
+         p += (long long)gridDim.x * blockDim.x) {
+        const long long vi = vlist ? (long long)vlist[p * stride] : p * stride;
+        for (int k = 0; k < 3; ++k) { const float c = mov[3 * vi + k]; lo[k] = fminf(lo[k], c); hi[k] = fmaxf(hi[k], c); }
+    }
+    __shared__ float sh[6][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < 3; ++k) {
+        float a = lo[k], b = hi[k];
+        for (int o = 16; o > 0; o >>= 1) {
+            a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+            b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        }
+        if (lane == 0) { sh[k][warp] = a; sh[3 + k][warp] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        float v = sh[k][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = (k < 3) ? fminf(v, sh[k][w]) : fmaxf(v, sh[k][w]);
+        part[blockIdx.x * 6 + k] = v;
+    }
+}
+__global__ void k_query_codes(const float* __restrict__ mov, const int* __restrict__ vlist, int stride,
+                              long long n_q, const float* __restrict__ bbox,
+                              unsigned long long* __restrict__ codes, uint32_t* __restrict__ pos)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_q) return;
+    const long long vi = vlist ? (long long)vlist[p * stride] : p * stride;
+    uint32_t g[3];
+    for (int k = 0; k < 3; ++k) {
+        const float ext = bbox[3 + k] - bbox[k];
+        float t = ext > 0.0f ? (mov[3 * vi + k] - bbox[k]) / ext : 0.0f;
+        t = fminf(fmaxf(t, 0.0f), 1.0f);
+        g[k] = (uint32_t)fminf(t * 2097152.0f, 2097151.0f);
+    }
+    codes[p] = morton_expand21(g[0]) | (morton_expand21(g[1]) << 1) | (morton_expand21(g[2]) << 2);
+    pos[p] = (uint32_t)p;
+}
+__global__ void k_invert_permutation(const uint32_t* __restrict__ slot_pos, long long n, uint32_t* __restrict__ pos_slot)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) pos_slot[slot_pos[t]] = (uint32_t)t;
 }
 
 // ---- percentile (reject_fraction) : exact radix select of the K-th smallest composite key
@@ -111,7 +185,8 @@ __global__ void k_select_init(DevState* st, long long rank, unsigned int* hist)
     }
 }
 __global__ void k_select_hist(const DevState* __restrict__ st,
-                              const unsigned long long* __restrict__ keys, long long n, int byte,
+                              const unsigned long long* __restrict__ keys,
+                              const uint32_t* __restrict__ slot_pos, long long n, int byte,
                               unsigned int* __restrict__ hist)
 {
     if (st->converged) return;
@@ -119,9 +194,10 @@ __global__ void k_select_hist(const DevState* __restrict__ st,
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const unsigned long long prefix = st->sel_prefix, mask = st->sel_mask;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
-         p += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long c = (keys[p] & 0xFFFFFFFF00000000ull) | (unsigned long long)p;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long p = slot_pos ? (unsigned long long)slot_pos[t] : (unsigned long long)t;
+        const unsigned long long c = (keys[t] & 0xFFFFFFFF00000000ull) | p;
         if ((c & mask) == prefix) atomicAdd(&sh[(c >> (8 * byte)) & 0xFF], 1u);
     }
     __syncthreads();
@@ -173,11 +249,12 @@ __device__ __forceinline__ PairEval eval_pair(const DevState* __restrict__ st,
                                               const unsigned long long* __restrict__ keys,
                                               const float4* __restrict__ base4, long long base_off,
                                               long long n_local, double thresh, int use_select,
-                                              long long p)
+                                              long long t, long long p)
 {
+    // t = slot (where q and the key live), p = query position (what vlist and the percentile use)
     PairEval e;
     e.keep = false;
-    const unsigned long long key = keys[p];
+    const unsigned long long key = keys[t];
     if (key == KEY_NONE) return e;
     const long long j = (long long)(uint32_t)(key & 0xFFFFFFFFull) - base_off;
     if (j < 0 || j >= n_local) return e;                        // another rank owns this target
@@ -187,7 +264,7 @@ __device__ __forceinline__ PairEval eval_pair(const DevState* __restrict__ st,
     }
     const float4 co1 = base4[j];
     float wqx, wqy, wqz, w1x, w1y, w1z;
-    s1_matvec(st->mw_base, qx[p], qy[p], qz[p], wqx, wqy, wqz);
+    s1_matvec(st->mw_base, qx[t], qy[t], qz[t], wqx, wqy, wqz);
     s1_matvec(st->mw_base, co1.x, co1.y, co1.z, w1x, w1y, w1z);
     e.dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
     if (!(e.dist < thresh)) return e;                            // strict, general.py:302
@@ -204,17 +281,19 @@ k_filter_moments(const DevState* __restrict__ st, const float* __restrict__ mov,
                  const float* __restrict__ qx, const float* __restrict__ qy,
                  const float* __restrict__ qz, const unsigned long long* __restrict__ keys,
                  const float4* __restrict__ base4, long long base_off, long long n_local,
-                 double thresh, int use_select, double* __restrict__ partials)
+                 double thresh, int use_select, const uint32_t* __restrict__ slot_pos,
+                 double* __restrict__ partials)
 {
     if (st->converged) return;
     double acc[MOM];
 #pragma unroll
     for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
     const double s0 = st->shift[0], s1 = st->shift[1], s2 = st->shift[2];
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_q;
-         p += (long long)gridDim.x * blockDim.x) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_q;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long p = slot_pos ? (long long)slot_pos[t] : t;
         const PairEval e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off,
-                                     n_local, thresh, use_select, p);
+                                     n_local, thresh, use_select, t, p);
         if (!e.keep) continue;
         const double a0 = (double)e.ax - s0, a1 = (double)e.ay - s1, a2 = (double)e.az - s2;
         const double b0 = (double)e.bx - s0, b1 = (double)e.by - s1, b2 = (double)e.bz - s2;
@@ -399,13 +478,15 @@ k_pairs_count(const DevState* __restrict__ st, const float* __restrict__ mov,
               const float* __restrict__ qy, const float* __restrict__ qz,
               const unsigned long long* __restrict__ keys, const float4* __restrict__ base4,
               long long base_off, long long n_local, double thresh, int use_select,
+              const uint32_t* __restrict__ pos_slot,
               unsigned char* __restrict__ flags, long long* __restrict__ block_counts)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false;
     if (p < n_q) {
+        const long long t = pos_slot ? (long long)pos_slot[p] : p;
         keep = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off, n_local, thresh,
-                         use_select, p).keep;
+                         use_select, t, p).keep;
         flags[p] = keep ? 1 : 0;
     }
     const int c = __syncthreads_count(keep ? 1 : 0);
@@ -427,6 +508,7 @@ k_pairs_emit(const DevState* __restrict__ st, const float* __restrict__ mov,
              const float* __restrict__ qy, const float* __restrict__ qz,
              const unsigned long long* __restrict__ keys, const float4* __restrict__ base4,
              long long base_off, long long n_local, double thresh, int use_select,
+             const uint32_t* __restrict__ pos_slot,
              const long long* __restrict__ block_offsets, long long K, double* __restrict__ A,
              double* __restrict__ B, double* __restrict__ dist_out)
 {
@@ -435,7 +517,7 @@ k_pairs_emit(const DevState* __restrict__ st, const float* __restrict__ mov,
     e.keep = false;
     if (p < n_q)
         e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off, n_local, thresh,
-                      use_select, p);
+                      use_select, pos_slot ? (long long)pos_slot[p] : p, p);
     __shared__ int warp_counts[EMIT_THREADS / 32];
     const unsigned ballot = __ballot_sync(0xffffffffu, e.keep);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -483,12 +565,13 @@ __global__ void k_dist_stats(const double* __restrict__ dist, long long K, doubl
     }
 }
 
-__global__ void k_unpack_keys(const unsigned long long* __restrict__ keys, long long n,
+__global__ void k_unpack_keys(const unsigned long long* __restrict__ keys,
+                              const uint32_t* __restrict__ pos_slot, long long n,
                               int* __restrict__ idx, float* __restrict__ d2)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const unsigned long long k = keys[p];
+    const unsigned long long k = keys[pos_slot ? (long long)pos_slot[p] : p];
     if (idx) idx[p] = (k == KEY_NONE) ? -1 : (int)(uint32_t)(k & 0xFFFFFFFFull);
     if (d2) d2[p] = __uint_as_float((uint32_t)(k >> 32));
 }
@@ -585,6 +668,18 @@ struct icp_handle {
     long long n_local = 0, n_global = 0, base_off = 0;
     int n_tiles = 0;
     bool have_base = false;
+    // spatial index (nn_mode == ICP_NN_BVH), built lazily from d_base4
+    BvhNode* d_bvh_nodes = nullptr;
+    float4* d_bvh_sorted = nullptr;
+    int bvh_P = 0;
+    bool bvh_built = false;
+    // query slots in Morton order of the moving vertices (BVH mode) + warm start bookkeeping
+    uint32_t* d_slot_pos = nullptr;
+    uint32_t* d_pos_slot = nullptr;
+    long long order_capacity = 0;
+    bool order_valid = false;
+    int order_stride = 0;
+    bool warm_valid = false;       // d_keys hold last iteration's winners for the current slots
     // moving
     float* d_mov = nullptr;
     long long mov_capacity = 0, n_vertices = 0;
@@ -753,6 +848,124 @@ int launch_nn(icp_handle* h, long long n_q)
     }
 }
 
+// ---- spatial index build (one-time per base, the BVHTree.FromObject equivalent) -----------------
+int build_bvh(icp_handle* h)
+{
+    if (h->bvh_built) return ICP_OK;
+    if (h->d_bvh_nodes) { cudaFree(h->d_bvh_nodes); h->d_bvh_nodes = nullptr; }
+    if (h->d_bvh_sorted) { cudaFree(h->d_bvh_sorted); h->d_bvh_sorted = nullptr; }
+    const long long n = h->n_local;
+    h->bvh_P = 0;
+    if (n <= 0) { h->bvh_built = true; return ICP_OK; }
+    const int n_runs = (int)((n + BVH_LEAF - 1) / BVH_LEAF);
+    const long long n_pad = (long long)n_runs * BVH_LEAF;
+    unsigned long long *codes = nullptr, *codes_out = nullptr, *run_keys = nullptr;
+    uint32_t *order = nullptr, *order_out = nullptr;
+    int* leaf_parent = nullptr;
+    float *part = nullptr, *bbox = nullptr;
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
+    const int pb = std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
+    CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n * 8));
+    CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n * 8));
+    CUDA_TRY(h, cudaMalloc((void**)&order, (size_t)n * 4));
+    CUDA_TRY(h, cudaMalloc((void**)&order_out, (size_t)n * 4));
+    CUDA_TRY(h, cudaMalloc((void**)&run_keys, (size_t)n_runs * 8));
+    CUDA_TRY(h, cudaMalloc((void**)&leaf_parent, (size_t)n_runs * 4));
+    CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 6 * 4));
+    CUDA_TRY(h, cudaMalloc((void**)&bbox, 6 * 4));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_bvh_sorted, (size_t)n_pad * sizeof(float4)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_bvh_nodes, (size_t)std::max(1, n_runs - 1) * sizeof(BvhNode)));
+    k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
+    k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+    k_morton_codes<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order);
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
+    CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
+    k_bvh_gather<<<(unsigned)((n_pad + 255) / 256), 256, 0, h->stream>>>(h->d_base4, order_out, n, n_pad, h->d_bvh_sorted);
+    k_run_keys<<<(unsigned)((n_runs + 255) / 256), 256, 0, h->stream>>>(codes_out, n, n_runs, run_keys);
+    if (n_runs > 1) {
+        k_lbvh_topology<<<(unsigned)((n_runs + 127) / 128), 128, 0, h->stream>>>(run_keys, n_runs, h->d_bvh_nodes, leaf_parent);
+        k_lbvh_fit<<<(unsigned)((n_runs + 127) / 128), 128, 0, h->stream>>>(h->d_bvh_sorted, n, n_runs, h->d_bvh_nodes, leaf_parent);
+    }
+    h->launches += 8;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(codes); cudaFree(codes_out); cudaFree(order); cudaFree(order_out);
+    cudaFree(run_keys); cudaFree(leaf_parent);
+    cudaFree(part); cudaFree(bbox); cudaFree(temp);
+    const int P = n_runs;
+    h->bvh_P = P;
+    h->bvh_built = true;
+    return ICP_OK;
+}
+
+int launch_nn_bvh(icp_handle* h, long long n_q)
+{
+    if (n_q <= 0 || h->n_local <= 0) return ICP_OK;
+    int rc = build_bvh(h);
+    if (rc) return rc;
+    ProfScope ps(h, 0);
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    if (h->prm.nn_variant == 99) {   // debug: count node / leaf visits (icp_debug_counters)
+        k_nn_bvh<true><<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz,
+                                                                            n_q, h->d_keys, (uint32_t)h->base_off,
+                                                                            &h->d_state->converged);
+    } else {
+        k_nn_bvh<false><<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz,
+                                                                             n_q, h->d_keys, (uint32_t)h->base_off,
+                                                                             &h->d_state->converged);
+    }
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+// slot order of the queries (one-time per icp_set_moving / stride change, BVH mode only)
+int ensure_query_order(icp_handle* h, long long n_q)
+{
+    const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
+    if (h->order_valid && h->order_stride == stride) return ICP_OK;
+    h->warm_valid = false;
+    if (n_q > h->order_capacity || !h->d_slot_pos) {
+        if (h->d_slot_pos) cudaFree(h->d_slot_pos);
+        if (h->d_pos_slot) cudaFree(h->d_pos_slot);
+        h->d_slot_pos = h->d_pos_slot = nullptr;
+        const long long cap = std::max<long long>(n_q, 1);
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_slot_pos, (size_t)cap * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_pos_slot, (size_t)cap * 4));
+        h->order_capacity = cap;
+    }
+    if (n_q > 0) {
+        unsigned long long *codes = nullptr, *codes_out = nullptr;
+        uint32_t* pos = nullptr;
+        float *part = nullptr, *bbox = nullptr;
+        void* temp = nullptr;
+        size_t temp_bytes = 0;
+        const int* vl = h->has_vlist ? h->d_vlist : nullptr;
+        const int pb = (int)std::min<long long>((n_q + 255) / 256, (long long)h->sm_count * 4);
+        CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n_q * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n_q * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&pos, (size_t)n_q * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 6 * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&bbox, 6 * 4));
+        k_query_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_mov, vl, stride, n_q, part);
+        k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+        k_query_codes<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_mov, vl, stride, n_q, bbox, codes, pos);
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, pos, h->d_slot_pos, (int)n_q, 0, 63, h->stream));
+        CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, pos, h->d_slot_pos, (int)n_q, 0, 63, h->stream));
+        k_invert_permutation<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_slot_pos, n_q, h->d_pos_slot);
+        h->launches += 5;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(codes); cudaFree(codes_out); cudaFree(pos); cudaFree(part); cudaFree(bbox); cudaFree(temp);
+    }
+    h->order_valid = true;
+    h->order_stride = stride;
+    return ICP_OK;
+}
+
 int moments_grid(const icp_handle* h, long long n)
 {
     long long b = (n + MOM_THREADS - 1) / MOM_THREADS;
@@ -798,16 +1011,24 @@ int enqueue_nn(icp_handle* h, long long n_q)
     if (rc) return rc;
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
+    const bool bvh = h->prm.nn_mode == ICP_NN_BVH;
+    if (bvh) {
+        rc = ensure_query_order(h, n_q);
+        if (rc) return rc;
+    } else {
+        h->warm_valid = false;
+    }
     {
         ProfScope ps(h, 3);
         k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
         if (n_q > 0)
             k_transform_queries<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(
-                h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q, qx, qy, qz,
-                h->d_keys);
+                h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q,
+                bvh ? h->d_slot_pos : nullptr, qx, qy, qz, h->d_keys,
+                (bvh && h->warm_valid) ? 1 : 0, h->d_base4, h->base_off, h->n_local);
         h->launches += 2;
     }
-    rc = launch_nn(h, n_q);
+    rc = (h->prm.nn_mode == ICP_NN_BVH) ? launch_nn_bvh(h, n_q) : launch_nn(h, n_q);
     if (rc) return rc;
     if (h->prm.world_size > 1 && n_q > 0) {
         if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
@@ -815,13 +1036,14 @@ int enqueue_nn(icp_handle* h, long long n_q)
         NCCL_TRY(h, g_nccl.AllReduce(h->d_keys, h->d_keys, (size_t)n_q, ncclUint64, ncclMin, h->comm,
                                      h->stream));
     }
+    h->warm_valid = bvh;          // d_keys now hold this pass's winners, slot-aligned
     if (h->prm.reject_fraction > 0 && n_q > 0) {
         ProfScope ps(h, 1);
         const long long keep = n_q - (long long)std::floor(h->prm.reject_fraction * (double)n_q);
         k_select_init<<<1, 256, 0, h->stream>>>(h->d_state, keep - 1, h->d_hist);
         const int g = (int)std::min<long long>((n_q + 255) / 256, (long long)h->sm_count * 8);
         for (int byte = 7; byte >= 0; --byte) {
-            k_select_hist<<<g, 256, 0, h->stream>>>(h->d_state, h->d_keys, n_q, byte, h->d_hist);
+            k_select_hist<<<g, 256, 0, h->stream>>>(h->d_state, h->d_keys, bvh ? h->d_slot_pos : nullptr, n_q, byte, h->d_hist);
             k_select_pick<<<1, 256, 0, h->stream>>>(h->d_state, byte, h->d_hist);
         }
         h->launches += 17;
@@ -842,7 +1064,8 @@ int enqueue_iteration(icp_handle* h, long long n_q)
         k_filter_moments<<<g, MOM_THREADS, 0, h->stream>>>(
             h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q, qx, qy, qz,
             h->d_keys, h->d_base4, h->base_off, h->n_local, h->prm.thresh,
-            h->prm.reject_fraction > 0 ? 1 : 0, h->d_partials);
+            h->prm.reject_fraction > 0 ? 1 : 0,
+            h->prm.nn_mode == ICP_NN_BVH ? h->d_slot_pos : nullptr, h->d_partials);
         k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
         h->launches += 2;
     }
@@ -983,7 +1206,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1016,6 +1239,8 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
     h->n_tiles = (int)((n_local + NN_TILE - 1) / NN_TILE);
     const long long n_pad = (long long)h->n_tiles * NN_TILE;
     h->n_local = n_local; h->n_global = n_global; h->base_off = global_offset;
+    h->bvh_built = false;
+    h->warm_valid = false;
     if (n_local > 0) {
         float* d_raw = nullptr;
         CUDA_TRY(h, cudaMalloc((void**)&h->d_base_tiles, (size_t)n_pad * 3 * sizeof(float)));
@@ -1043,6 +1268,8 @@ int icp_set_moving(icp_handle* h, const float* xyz, int64_t n_vertices, const in
     if (n_vertices > 0)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_mov, xyz, (size_t)n_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     h->n_vertices = n_vertices;
+    h->order_valid = false;
+    h->warm_valid = false;
     h->has_vlist = vlist != nullptr;
     h->n_vlist = n_vlist;
     double shift[3] = {0, 0, 0};
@@ -1123,7 +1350,7 @@ int icp_nn(icp_handle* h, int32_t* idx, float* d2)
         int* d_idx = nullptr; float* d_d2 = nullptr;
         if (idx) CUDA_TRY(h, cudaMalloc((void**)&d_idx, (size_t)n_q * sizeof(int)));
         if (d2) CUDA_TRY(h, cudaMalloc((void**)&d_d2, (size_t)n_q * sizeof(float)));
-        k_unpack_keys<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_keys, n_q, d_idx, d_d2);
+        k_unpack_keys<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_keys, h->prm.nn_mode == ICP_NN_BVH ? h->d_pos_slot : nullptr, n_q, d_idx, d_d2);
         h->launches++;
         if (idx) CUDA_TRY(h, cudaMemcpyAsync(idx, d_idx, (size_t)n_q * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         if (d2) CUDA_TRY(h, cudaMemcpyAsync(d2, d_d2, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1167,9 +1394,10 @@ int icp_make_pairs(icp_handle* h, int calc_stats, double* A, double* B, int64_t 
     const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
     const int* vl = h->has_vlist ? h->d_vlist : nullptr;
     const int use_sel = h->prm.reject_fraction > 0 ? 1 : 0;
+    const uint32_t* pos_slot = h->prm.nn_mode == ICP_NN_BVH ? h->d_pos_slot : nullptr;
     k_pairs_count<<<nb, EMIT_THREADS, 0, h->stream>>>(h->d_state, h->d_mov, vl, stride, n_q, qx, qy, qz,
                                                       h->d_keys, h->d_base4, h->base_off, h->n_local,
-                                                      h->prm.thresh, use_sel, h->d_flags, h->d_block_counts);
+                                                      h->prm.thresh, use_sel, pos_slot, h->d_flags, h->d_block_counts);
     k_scan_counts<<<1, 32, 0, h->stream>>>(h->d_block_counts, nb, h->d_total);
     h->launches += 2;
     long long K = 0;
@@ -1190,7 +1418,7 @@ int icp_make_pairs(icp_handle* h, int calc_stats, double* A, double* B, int64_t 
         double* dA = h->d_pairs; double* dB = dA + 3 * K; double* dD = dB + 3 * K; double* dS = dD + K;
         k_pairs_emit<<<nb, EMIT_THREADS, 0, h->stream>>>(h->d_state, h->d_mov, vl, stride, n_q, qx, qy, qz,
                                                          h->d_keys, h->d_base4, h->base_off, h->n_local,
-                                                         h->prm.thresh, use_sel, h->d_block_counts, K, dA, dB, dD);
+                                                         h->prm.thresh, use_sel, pos_slot, h->d_block_counts, K, dA, dB, dD);
         h->launches++;
         // A, B have row stride K on the device; the caller's have row stride `capacity`
         CUDA_TRY(h, cudaMemcpy2DAsync(A, (size_t)capacity * sizeof(double), dA, (size_t)K * sizeof(double),
@@ -1433,6 +1661,21 @@ int icp_flush_l2(icp_handle* h)
     int rc = ensure_scratch(h, bytes);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemsetAsync(h->d_scratch, 0, bytes, h->stream));
+    return ICP_OK;
+}
+
+int icp_debug_counters(icp_handle* h, uint64_t out[4], int reset)
+{
+    if (!h || !out) return ICP_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    unsigned long long v[4] = {0, 0, 0, 0};
+    CUDA_TRY(h, cudaMemcpyFromSymbol(v, g_bvh_counters, sizeof(v)));
+    for (int i = 0; i < 4; ++i) out[i] = v[i];
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        CUDA_TRY(h, cudaMemcpyToSymbol(g_bvh_counters, z, sizeof(z)));
+    }
     return ICP_OK;
 }
 

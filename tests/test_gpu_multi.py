@@ -23,7 +23,7 @@ dist = icpdist.init_rendezvous("gloo")
 cfg = meshgen.config_cloud(60_000, 90_001, 51, 52)
 rf = float(os.environ.get("ICP_RF", "0"))
 eng = IcpEngine(thresh=0.5, use_target=True, target_d=1e-4, device=local, rank=rank, world_size=world,
-                reject_fraction=rf)
+                reject_fraction=rf, nn_mode=int(os.environ.get("ICP_NN_MODE", "0")))
 eng.set_base_sharded(cfg["base"])
 icpdist.connect_engine(eng, dist)
 eng.set_moving(cfg["moving"])
@@ -44,8 +44,8 @@ def _gpu_count():
     return _native.lib().icp_device_count()
 
 
-@pytest.mark.parametrize("rf", [0.0, 0.2])
-def test_sharded_base_matches_single_gpu(tmp_path, rf):
+@pytest.mark.parametrize("rf,nn_mode", [(0.0, 0), (0.2, 0), (0.0, 1), (0.2, 1)])
+def test_sharded_base_matches_single_gpu(tmp_path, rf, nn_mode):
     n = _gpu_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -55,7 +55,7 @@ def test_sharded_base_matches_single_gpu(tmp_path, rf):
     outs = {}
     for w in (1, world):
         out = tmp_path / ("out%d.npz" % w)
-        env = dict(os.environ, ICP_OUT=str(out), ICP_RF=str(rf))
+        env = dict(os.environ, ICP_OUT=str(out), ICP_RF=str(rf), ICP_NN_MODE=str(nn_mode))
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(w),
                "--master-addr", "127.0.0.1", "--master-port", str(29600 + w), str(script)]
         subprocess.run(cmd, check=True, env=env, timeout=600, cwd=ROOT)

@@ -141,6 +141,110 @@ def test_nn_full_size_properties_1m():
     assert np.array_equal(np.minimum.reduce(keys), orc.pack_key(d2[:50_000], idx[:50_000]))
 
 
+# ------------------------------------------------------------------ N2: BVH search == brute force
+def _clouds_for_bvh(case):
+    rng = np.random.default_rng(77)
+    if case == "surface":
+        cfg = meshgen.config_cloud(40_000, 60_000, 61, 62)
+        return cfg["base"], cfg["moving"]
+    if case == "far_outliers":            # queries far outside the base's bounding box
+        cfg = meshgen.config_cloud(20_000, 50_000, 63, 64)
+        mov = cfg["moving"].copy()
+        mov[::3] = ((rng.random((len(mov[::3]), 3)) - 0.5) * 40).astype(np.float32)
+        return cfg["base"], mov
+    if case == "duplicates":              # many exact ties: lowest index must win
+        base = _rand_cloud(3000, 65)
+        base = np.concatenate([base, base[::-1], base[:1500]])
+        return base, np.concatenate([base[::7], _rand_cloud(5000, 66)])
+    if case == "collinear":               # degenerate extent (all on a line / a plane)
+        t = rng.random(20_000).astype(np.float32)
+        base = np.stack([t, np.zeros_like(t), np.zeros_like(t)], axis=1)
+        return base, _rand_cloud(4000, 67, 0.5)
+    if case == "volume":
+        return _rand_cloud(70_001, 68), _rand_cloud(30_000, 69, 1.5)
+    if case == "lattice":                 # regular grid: massive numbers of equidistant ties
+        g = np.arange(24, dtype=np.float32)
+        base = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+        mov = (base[::5] + np.float32(0.5)).astype(np.float32)
+        return base, np.concatenate([mov, base[::11]])
+    raise KeyError(case)
+
+
+@pytest.mark.parametrize("case", ["surface", "far_outliers", "duplicates", "collinear", "volume", "lattice"])
+def test_bvh_matches_bruteforce_oracle(case):
+    base, mov = _clouds_for_bvh(case)
+    with IcpEngine(nn_mode=1) as e:
+        e.set_base(base)
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+    oi, od = orc.nn_bruteforce(mov, base)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+
+
+@pytest.mark.parametrize("n_base,n_mov", [(1, 1), (1, 300), (7, 9), (8, 8), (9, 100), (1023, 1),
+                                          (1025, 1025), (4097, 2049)])
+def test_bvh_ragged_sizes(n_base, n_mov):
+    base = _rand_cloud(n_base, 10 + n_base)
+    mov = _rand_cloud(n_mov, 20 + n_mov)
+    with IcpEngine(nn_mode=1) as e:
+        e.set_base(base)
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+        e.set_base(np.zeros((0, 3), np.float32))
+        assert (e.nn()[0] == -1).all()
+    oi, od = orc.nn_bruteforce(mov, base)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+
+
+def test_bvh_equals_bruteforce_kernel_at_1m():
+    """Full C3 size: every one of the 1M keys from the BVH search equals the brute-force kernel's,
+    before alignment (offset clouds) -- and the sharded form composes by MIN as well."""
+    cfg = meshgen.config_cloud(1_000_000, 1_000_000, 200, 201)
+    res = {}
+    for mode in (0, 1):
+        with IcpEngine(nn_mode=mode) as e:
+            e.set_base(cfg["base"])
+            e.set_moving(cfg["moving"])
+            e.set_matrices(np.eye(4), np.eye(4))
+            res[mode] = e.nn()
+            if mode == 1:
+                keys = []
+                for lo, hi in ((0, 400_000), (400_000, 1_000_000)):
+                    e.set_base(cfg["base"][lo:hi], lo, 1_000_000)
+                    i, d = e.nn()
+                    keys.append(orc.pack_key(d, i))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(np.minimum.reduce(keys), orc.pack_key(res[0][1], res[0][0]))
+
+
+@pytest.mark.parametrize("name", ["c1_fixed20", "c1_worldmats", "cloud_2k_3k", "c1_defaults"])
+def test_bvh_trajectory_matches_bruteforce(name):
+    g = Golden(name)
+    p = g.prefs
+    vlist = orc.build_vlist_port(g.moving.shape[0], g.groups)
+    out = {}
+    for mode in (0, 1):
+        with IcpEngine(thresh=p["min_start"], target_d=p["target_d"], use_target=p["use_target"],
+                       align_meth=p["align_meth"], stride=orc.stride_factor_port(p["sample_fraction"]),
+                       nn_mode=mode) as e:
+            e.set_base(g.base)
+            e.set_moving(g.moving, vlist)
+            e.set_matrices(g.mw_align, g.mw_base)
+            done, conv, recs = e.run(p["icp_iterations"])
+            out[mode] = (done, conv, e.matrix_world(), [r.M for r in recs], [r.pairs for r in recs])
+    assert out[0][0] == out[1][0] == g.iterations and out[0][1] == out[1][1] == g.converged
+    # same keys every iteration; the fp64 moments are summed in slot (Morton) order in BVH mode,
+    # so M may differ in the last bits and the composed fp32 pose by an ulp
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=0, atol=1e-6)
+    assert out[0][4] == out[1][4]
+    for a, b in zip(out[0][3], out[1][3]):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(out[1][2], g.matrix_world, atol=1e-5)
+
+
 # ------------------------------------------------------------------ make_pairs / solver API
 def _objects(g):
     align = ms.Object("align", g.moving, g.mw_align, g.groups)
@@ -249,6 +353,25 @@ def test_stepwise_parity_against_oracle(name):
             np.testing.assert_allclose(st.angle, orc.rotation_angle(Mo.astype(np.float32)), atol=1e-6)
             # pose update: matrix_world @ fp32(M) with rule S3, bit-exact given the engine's M
             np.testing.assert_array_equal(e.matrix_world(), ms.matmul44(mw, M.astype(np.float32)))
+
+
+def test_bvh_warm_start_stays_exact_over_iterations():
+    """BVH mode re-uses last iteration's winner as the initial bound; every iteration's keys must
+    still equal the brute-force oracle evaluated at the engine's own current pose."""
+    cfg = meshgen.config_cloud(50_000, 80_000, 71, 72)
+    with IcpEngine(thresh=0.5, use_target=False, nn_mode=1) as e:
+        e.set_base(cfg["base"])
+        e.set_moving(cfg["moving"])
+        e.set_matrices(np.eye(4), np.eye(4))
+        for it in range(6):
+            mw = e.matrix_world()
+            res = orc.make_pairs_vec(cfg["moving"], np.arange(50_000), mw, np.eye(4), cfg["base"], 0.5, 1,
+                                     return_all=True, nn="kdtree")
+            idx, d2 = e.nn()                     # warm-started from the previous pass
+            assert np.array_equal(idx, res["idx"]) and np.array_equal(d2, res["d2"])
+            M, st = e.step()
+            assert st.pairs == int(res["keep"].sum())
+            np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(res["A"], res["B"]), atol=1e-10)
 
 
 def test_reference_shaped_loop_with_icp_step():
