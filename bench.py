@@ -219,8 +219,10 @@ def run_ours(args, rank, world, local_rank):
     m, n = mov.shape[0], base.shape[0]
     ident = np.eye(4, dtype=np.float32)
 
+    nn_mode = 1 if args.nn_mode == "bvh" else 0
     eng = IcpEngine(thresh=cfg["thresh"], use_target=False, align_meth="0", stride=1,
-                    device=local_rank, rank=rank, world_size=world, nn_variant=args.nn_variant)
+                    device=local_rank, rank=rank, world_size=world, nn_variant=args.nn_variant,
+                    nn_mode=nn_mode)
     t0 = time.perf_counter()
     eng.set_base_sharded(base)
     base_upload_s = time.perf_counter() - t0
@@ -309,7 +311,9 @@ def run_ours(args, rank, world, local_rank):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "nn_traffic.json"))).get(args.workload)
     except (OSError, ValueError):
         pass
-    roofline = {
+    if nn_mode == 1:
+        line_roofline = bvh_roofline(m, n_local, nn_avg_ms, hbm_peak_of(peaks), args.workload)
+    roofline = line_roofline if nn_mode == 1 else {
         "kernel": "k_nn_bruteforce", "bound": "fp32",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "traffic": traffic,
@@ -322,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
                        "%.1e pair evaluations (SURVEY D4)" % ((12 * n_local + 52 * m) / 1e6, float(m) * n_local),
     }
     stream_bytes = 12.0 * n_local + 52.0 * m
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_peak = hbm_peak_of(peaks)
     mom_avg_ms = mom_ms / max(mom_launches, 1)
     roofline_streaming = {
         "kernel": "k_filter_moments(+reduce)", "bound": "hbm",
@@ -341,7 +345,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][4], "n_moving": m, "n_base": n,
                    "base_shards": world, "thresh": cfg["thresh"], "sample_fraction": 1.0,
-                   "align_meth": "RIGID", "nn_mode": "bruteforce", "nn_variant": args.nn_variant,
+                   "align_meth": "RIGID", "nn_mode": args.nn_mode, "nn_variant": args.nn_variant,
                    "l2": "flushed between timed steps (256 MB memset)",
                    "collectives": "ncclAllReduce MIN u64[M] + SUM f64[20] per step" if world > 1 else "none"},
         "correspondences_per_sec": value * m,
@@ -358,11 +362,75 @@ def run_ours(args, rank, world, local_rank):
         "pairs_kept_last": int(pairs[-1]) if pairs else None,
         "final_pose_row0": [float(x) for x in final_pose[0]],
     }
+    eng.close()
+    if world == 1 and not args.no_secondary:
+        other = 0 if nn_mode == 1 else 1
+        line["next_rows" if other == 1 else "north_star_kernel"] = {
+            ("N2_bvh_search" if other == 1 else "bruteforce"): measure_secondary(
+                cfg, local_rank, other, args.steps if other == 1 else min(args.steps, 5), 3)}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(cfg, args.cpu_sample, 2)
         line["cpu_fair"] = cpu_fair_comparator(cfg)
-    eng.close()
     print(json.dumps(line), flush=True)
+
+
+def hbm_peak_of(peaks):
+    return peaks.get("hbm_gbs", 6650.0)
+
+
+def bvh_roofline(m, n_local, avg_ms, hbm_peak, workload):
+    """Roofline of k_nn_bvh: compulsory DRAM bytes per launch = queries in (12 B) + keys read and
+    written (16 B) per query + one pass over the tree (64 B per 8-vertex run) and the sorted
+    vertices (16 B each).  The tree walk itself is served by L1/L2 (the index of a 1M-vertex base
+    is 24 MB against a 126 MB L2), so this fraction is small by construction; the walk's requested
+    bytes are reported beside it."""
+    compulsory = 28.0 * m + (16.0 + 8.0) * n_local
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "nn_traffic.json"))).get(workload + "_bvh")
+    except (OSError, ValueError):
+        pass
+    ach = compulsory / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
+    return {"kernel": "k_nn_bvh", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+            "frac": ach / hbm_peak if ach else None, "traffic": traffic,
+            "algorithmic": "28 B per query + 24 B per base vertex (index read once)",
+            "avg_launch_ms": avg_ms, "queries_per_s": m / (avg_ms * 1e-3) if avg_ms > 0 else None,
+            "note": "latency/L2-bound tree walk: ~48 node visits x 64 B + ~8 leaves x 128 B requested per "
+                    "query, served from L1/L2"}
+
+
+def measure_secondary(cfg, local_rank, mode, steps, warmup):
+    """Same resident measurement for the other NN mode on one GPU (reported beside the primary)."""
+    from object_alignment_b200 import IcpEngine
+
+    ident = np.eye(4, dtype=np.float32)
+    with IcpEngine(thresh=cfg["thresh"], use_target=False, device=local_rank, nn_mode=mode) as e:
+        e.set_base(cfg["base"])
+        e.set_moving(cfg["moving"])
+        e.set_matrices(ident, ident)
+        for _ in range(warmup):
+            e.run(1)
+        e.set_matrices(ident, ident)
+        e.reset_convergence()
+        e.set_profiling(True)
+        ms = []
+        for _ in range(steps):
+            e.flush_l2()
+            e.run(1)
+            ms.append(e.last_elapsed_ms())
+        nn_ms, nn_n = e.kernel_time_ms(0)
+        pose = e.matrix_world()
+        # whole 50-iteration operator-style run, device resident, no flushes
+        e.set_matrices(ident, ident)
+        e.reset_convergence()
+        e.set_profiling(False)
+        e.run(50)
+        run50 = e.last_elapsed_ms()
+    return {"nn_mode": "bvh" if mode == 1 else "bruteforce", "value": 1e3 * steps / sum(ms),
+            "unit": "iterations/s", "ms_per_step": sum(ms) / steps, "steps": steps,
+            "nn_avg_launch_ms": nn_ms / max(nn_n, 1), "ms_per_step_first": ms[0], "ms_per_step_last": ms[-1],
+            "run50_ms": run50, "run50_iterations_per_s": 50e3 / run50,
+            "final_pose_row0": [float(x) for x in pose[0]]}
 
 
 def main():
@@ -373,8 +441,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--nn-variant", type=int, default=0)
+    ap.add_argument("--nn-mode", default="bruteforce", choices=["bruteforce", "bvh"],
+                    help="bruteforce = the north-star O(M N) kernel (default, primary line); "
+                         "bvh = row N2, the exact spatially-indexed search")
     ap.add_argument("--cpu-sample", type=int, default=20_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

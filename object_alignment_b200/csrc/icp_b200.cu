@@ -28,33 +28,13 @@
 
 #include "../../include/icp_b200.h"
 #include "device_math.cuh"
+#include "icp_state.cuh"
 #include "nn_bruteforce.cuh"
 #include "nn_bvh.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
 namespace icp {
-
-constexpr int MOM = 20;          // K, sum a'(3), sum b'(3), sum b' a'^T (9), sum|a'|^2, sum|b'|^2, sum d, sum d^2
-constexpr int MOM_THREADS = 256;
-
-struct DevState {
-    float mw_align[16];
-    float mw_base[16];
-    float imx1[16];
-    float imx2[16];
-    double M[16];
-    double ring[5];
-    double shift[3];             // a0: moments are accumulated about this point (cancellation guard)
-    int n_iter;
-    int converged;               // also used as the "stop" flag read by every kernel
-    int error;                   // icp_status raised on the device (too few pairs, singular)
-    int pad;
-    unsigned long long sel_prefix, sel_mask, sel_threshold;
-    long long sel_rank;
-    int sel_valid;
-    int pad2;
-};
 
 // ------------------------------------------------------------------------------------------
 // small kernels
@@ -167,6 +147,15 @@ __global__ void k_query_codes(const float* __restrict__ mov, const int* __restri
     codes[p] = morton_expand21(g[0]) | (morton_expand21(g[1]) << 1) | (morton_expand21(g[2]) << 2);
     pos[p] = (uint32_t)p;
 }
+__global__ void k_gather_mov_slots(const float* __restrict__ mov, const int* __restrict__ vlist, int stride,
+                                   const uint32_t* __restrict__ slot_pos, long long n_q, float4* __restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_q) return;
+    const long long p = slot_pos[t];
+    const long long vi = vlist ? (long long)vlist[p * stride] : p * stride;
+    out[t] = make_float4(mov[3 * vi], mov[3 * vi + 1], mov[3 * vi + 2], __uint_as_float((uint32_t)p));
+}
 __global__ void k_invert_permutation(const uint32_t* __restrict__ slot_pos, long long n, uint32_t* __restrict__ pos_slot)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,13 +215,6 @@ __global__ void k_select_pick(DevState* st, int byte, unsigned int* hist)
 }
 
 // ---- K3 + K4 : filter and fp64 moments ------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 struct PairEval {
     bool keep;
     float ax, ay, az, bx, by, bz;
@@ -295,32 +277,9 @@ k_filter_moments(const DevState* __restrict__ st, const float* __restrict__ mov,
         const PairEval e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off,
                                      n_local, thresh, use_select, t, p);
         if (!e.keep) continue;
-        const double a0 = (double)e.ax - s0, a1 = (double)e.ay - s1, a2 = (double)e.az - s2;
-        const double b0 = (double)e.bx - s0, b1 = (double)e.by - s1, b2 = (double)e.bz - s2;
-        acc[0] += 1.0;
-        acc[1] += a0; acc[2] += a1; acc[3] += a2;
-        acc[4] += b0; acc[5] += b1; acc[6] += b2;
-        acc[7] += b0 * a0; acc[8] += b0 * a1; acc[9] += b0 * a2;
-        acc[10] += b1 * a0; acc[11] += b1 * a1; acc[12] += b1 * a2;
-        acc[13] += b2 * a0; acc[14] += b2 * a1; acc[15] += b2 * a2;
-        acc[16] += a0 * a0 + a1 * a1 + a2 * a2;
-        acc[17] += b0 * b0 + b1 * b1 + b2 * b2;
-        acc[18] += e.dist;
-        acc[19] += e.dist * e.dist;
+        moments_add(acc, e.ax, e.ay, e.az, e.bx, e.by, e.bz, e.dist, s0, s1, s2);
     }
-    __shared__ double sh[MOM_THREADS / 32][MOM];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < MOM; ++i) {
-        const double v = warp_sum(acc[i]);
-        if (lane == 0) sh[warp][i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < MOM) {
-        double v = 0.0;
-        for (int w = 0; w < MOM_THREADS / 32; ++w) v += sh[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * MOM + threadIdx.x] = v;
-    }
+    block_reduce_moments<MOM_THREADS>(acc, partials);
 }
 
 // moments of explicit pair arrays (affine_matrix_from_points entry; v0, v1 are 3 x K row-major)
@@ -676,6 +635,7 @@ struct icp_handle {
     // query slots in Morton order of the moving vertices (BVH mode) + warm start bookkeeping
     uint32_t* d_slot_pos = nullptr;
     uint32_t* d_pos_slot = nullptr;
+    float4* d_mov_slots = nullptr;         // moving vertices gathered into slot order (fused kernel input)
     long long order_capacity = 0;
     bool order_valid = false;
     int order_stride = 0;
@@ -907,14 +867,22 @@ int launch_nn_bvh(icp_handle* h, long long n_q)
     if (rc) return rc;
     ProfScope ps(h, 0);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
-    if (h->prm.nn_variant == 99) {   // debug: count node / leaf visits (icp_debug_counters)
-        k_nn_bvh<true><<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz,
-                                                                            n_q, h->d_keys, (uint32_t)h->base_off,
-                                                                            &h->d_state->converged);
-    } else {
-        k_nn_bvh<false><<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz,
-                                                                             n_q, h->d_keys, (uint32_t)h->base_off,
-                                                                             &h->d_state->converged);
+    const unsigned g128 = (unsigned)((n_q + 127) / 128);
+    const int v = h->prm.nn_variant;
+    if (v == 99) {          // debug: per-thread walk with visit counters (icp_debug_counters)
+        k_nn_bvh<true><<<g128, 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, n_q,
+                                                    h->d_keys, (uint32_t)h->base_off, &h->d_state->converged);
+    } else if (v == 10) {   // per-thread walk
+        k_nn_bvh<false><<<g128, 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, n_q,
+                                                     h->d_keys, (uint32_t)h->base_off, &h->d_state->converged);
+    } else if (v == 98) {   // debug: warp-packet walk with visit counters
+        k_nn_bvh_packet<false, true><<<g128, PKT_THREADS, 0, h->stream>>>(
+            h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0,
+            n_q, h->d_keys, (uint32_t)h->base_off, nullptr);
+    } else {                // default: warp-packet walk
+        k_nn_bvh_packet<false, false><<<g128, PKT_THREADS, 0, h->stream>>>(
+            h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0,
+            n_q, h->d_keys, (uint32_t)h->base_off, nullptr);
     }
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -930,10 +898,13 @@ int ensure_query_order(icp_handle* h, long long n_q)
     if (n_q > h->order_capacity || !h->d_slot_pos) {
         if (h->d_slot_pos) cudaFree(h->d_slot_pos);
         if (h->d_pos_slot) cudaFree(h->d_pos_slot);
+        if (h->d_mov_slots) cudaFree(h->d_mov_slots);
         h->d_slot_pos = h->d_pos_slot = nullptr;
+        h->d_mov_slots = nullptr;
         const long long cap = std::max<long long>(n_q, 1);
         CUDA_TRY(h, cudaMalloc((void**)&h->d_slot_pos, (size_t)cap * 4));
         CUDA_TRY(h, cudaMalloc((void**)&h->d_pos_slot, (size_t)cap * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_mov_slots, (size_t)cap * sizeof(float4)));
         h->order_capacity = cap;
     }
     if (n_q > 0) {
@@ -956,7 +927,8 @@ int ensure_query_order(icp_handle* h, long long n_q)
         CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
         CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, pos, h->d_slot_pos, (int)n_q, 0, 63, h->stream));
         k_invert_permutation<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_slot_pos, n_q, h->d_pos_slot);
-        h->launches += 5;
+        k_gather_mov_slots<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_mov, vl, stride, h->d_slot_pos, n_q, h->d_mov_slots);
+        h->launches += 6;
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(codes); cudaFree(codes_out); cudaFree(pos); cudaFree(part); cudaFree(bbox); cudaFree(temp);
@@ -1052,8 +1024,60 @@ int enqueue_nn(icp_handle* h, long long n_q)
     return ICP_OK;
 }
 
+int ensure_partials(icp_handle* h, int g)
+{
+    if (g > h->partials_capacity) {
+        if (h->d_partials) cudaFree(h->d_partials);
+        h->d_partials = nullptr;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_partials, (size_t)g * MOM * sizeof(double)));
+        h->partials_capacity = g;
+    }
+    return ICP_OK;
+}
+
+// BVH mode on one GPU without percentile cut: transform + search + filter + moments in ONE kernel
+int enqueue_iteration_fused(icp_handle* h, long long n_q)
+{
+    int rc = ensure_query_buffers(h, n_q);
+    if (rc) return rc;
+    rc = ensure_query_order(h, n_q);
+    if (rc) return rc;
+    rc = build_bvh(h);
+    if (rc) return rc;
+    const int g = (int)std::max<long long>(1, (n_q + PKT_THREADS - 1) / PKT_THREADS);
+    rc = ensure_partials(h, g);
+    if (rc) return rc;
+    {
+        ProfScope ps(h, 3);
+        k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
+        h->launches += 1;
+    }
+    {
+        ProfScope ps(h, 0);
+        k_nn_bvh_packet<true, false><<<g, PKT_THREADS, 0, h->stream>>>(
+            h->d_bvh_nodes, h->d_bvh_sorted, h->n_local > 0 ? h->bvh_P : 0, nullptr, nullptr, nullptr, h->d_state,
+            h->d_mov_slots, h->d_base4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
+            h->d_keys, (uint32_t)h->base_off, h->d_partials);
+        h->launches += 1;
+    }
+    h->warm_valid = true;
+    {
+        ProfScope ps(h, 2);
+        k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
+        k_solve_update<<<1, 32, 0, h->stream>>>(h->d_state, h->d_moments, h->prm.align_meth == 1,
+                                                h->prm.use_target, h->prm.target_d, h->d_stats,
+                                                h->stats_capacity);
+        h->launches += 2;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
 int enqueue_iteration(icp_handle* h, long long n_q)
 {
+    if (h->prm.nn_mode == ICP_NN_BVH && h->prm.world_size == 1 && !(h->prm.reject_fraction > 0) &&
+        h->prm.nn_variant != 10 && h->prm.nn_variant != 11 && h->prm.nn_variant != 99 && h->prm.nn_variant != 98)
+        return enqueue_iteration_fused(h, n_q);
     int rc = enqueue_nn(h, n_q);
     if (rc) return rc;
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
@@ -1206,7 +1230,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }

@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "device_math.cuh"
+#include "icp_state.cuh"
 
 namespace icp {
 
@@ -290,6 +291,160 @@ k_nn_bvh(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, i
         atomicAdd(&g_bvh_counters[1], (unsigned long long)c_leaf);
         atomicAdd(&g_bvh_counters[2], (unsigned long long)c_push);
         atomicAdd(&g_bvh_counters[3], 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-packet variant.  Query slots are in Morton order of the moving vertices, so the 32
+// queries of a warp are spatial neighbours and want nearly the same nodes.  The warp walks the
+// tree TOGETHER: one shared stack, node and leaf loads are warp-uniform (one transaction,
+// broadcast), every lane evaluates its own bounds and distances, and a subtree is entered when
+// ANY lane still needs it -- so there is no divergence.  Each lane's own prune test is exactly
+// the single-thread kernel's, hence the same exact result.
+//
+// FUSED (one GPU, no percentile): the kernel also does K1 (q = imx2 @ (mx1 @ a), warm start from
+// the previous winner) in its prologue and K3+K4 (world distance, thresh, target, fp64 moment
+// partials) in its epilogue, so an ICP iteration is this kernel + one single-CTA solve.
+// ---------------------------------------------------------------------------------------------
+constexpr int PKT_THREADS = 128;
+
+template <bool FUSED, bool COUNT>
+__global__ void __launch_bounds__(PKT_THREADS)
+k_nn_bvh_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
+                const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
+                const DevState* __restrict__ st, const float4* __restrict__ mov_slots,
+                const float4* __restrict__ base4, long long base_off, long long n_local, double thresh,
+                int warm, long long n_queries, unsigned long long* __restrict__ keys,
+                uint32_t index_offset, double* __restrict__ partials)
+{
+    if (st->converged) return;
+    __shared__ int s_ref[PKT_THREADS / 32][BVH_STACK];
+    __shared__ float s_bound[PKT_THREADS / 32][BVH_STACK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < n_queries;
+    const float inf = __int_as_float(0x7f800000);
+
+    float x = 0.f, y = 0.f, z = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    float wx = 0.f, wy = 0.f, wz = 0.f;                 // winner's coordinates (FUSED epilogue)
+    unsigned long long best = KEY_NONE;
+    if (active) {
+        if (FUSED) {
+            const float4 a = mov_slots[t];
+            ax = a.x; ay = a.y; az = a.z;
+            float tx, ty, tz;
+            s1_matvec(st->mw_align, ax, ay, az, tx, ty, tz);
+            s1_matvec(st->imx2, tx, ty, tz, x, y, z);
+            if (warm) {
+                const unsigned long long old = keys[t];
+                const long long j = (long long)(uint32_t)(old & 0xFFFFFFFFull) - base_off;
+                if (old != KEY_NONE && j >= 0 && j < n_local) {
+                    const float4 b = base4[j];
+                    const float d = s4_d2(x, y, z, b.x, b.y, b.z);
+                    if (d < inf) {
+                        best = ((unsigned long long)__float_as_uint(d) << 32) | (old & 0xFFFFFFFFull);
+                        wx = b.x; wy = b.y; wz = b.z;
+                    }
+                }
+            }
+        } else {
+            x = qx[t]; y = qy[t]; z = qz[t];
+            best = keys[t];
+        }
+    }
+    float best_d = (best == KEY_NONE) ? inf : __uint_as_float((uint32_t)(best >> 32));
+
+    int sp = 0;
+    int cur = (n_runs > 1) ? 0 : ~0;
+    unsigned int c_inner = 0, c_leaf = 0, c_push = 0;
+    const float4* nodes4 = reinterpret_cast<const float4*>(nodes);
+    if (n_runs > 0) {
+        while (true) {
+            if (cur < 0) {
+                const float4* lp = sorted + (long long)(~cur) * BVH_LEAF;
+                if (COUNT) ++c_leaf;
+#pragma unroll
+                for (int i = 0; i < BVH_LEAF; ++i) {
+                    const float4 b = __ldg(lp + i);                   // warp-uniform address
+                    const float d = s4_d2(x, y, z, b.x, b.y, b.z);
+                    if (d <= best_d && d < inf && active) {            // rare once the bound is tight
+                        const unsigned long long k =
+                            ((unsigned long long)__float_as_uint(d) << 32) |
+                            (unsigned long long)(index_offset + __float_as_uint(b.w));
+                        if (k < best) {
+                            best = k; best_d = d;
+                            if (FUSED) { wx = b.x; wy = b.y; wz = b.z; }
+                        }
+                    }
+                }
+            } else {
+                if (COUNT) ++c_inner;
+                const float4 n0 = __ldg(nodes4 + 4 * (long long)cur), n1 = __ldg(nodes4 + 4 * (long long)cur + 1);
+                const float4 n2 = __ldg(nodes4 + 4 * (long long)cur + 2), n3 = __ldg(nodes4 + 4 * (long long)cur + 3);
+                const float bl = box_lower_bound(x, y, z, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+                const float br = box_lower_bound(x, y, z, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+                const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+                const bool wl = active && !(bl * BVH_SHRINK > best_d) && bl < inf;
+                const bool wr = active && !(br * BVH_SHRINK > best_d) && br < inf;
+                const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
+                if (ml != 0u && mr != 0u) {
+                    // enter first the child most lanes would enter first; park the other with the
+                    // smallest bound any interested lane has for it
+                    const unsigned pl = __ballot_sync(0xffffffffu, wl && (!wr || bl <= br));
+                    const bool left_first = 2 * __popc(pl) >= __popc(ml | mr);
+                    const float fb = left_first ? (wr ? br : inf) : (wl ? bl : inf);
+                    const unsigned fmin = __reduce_min_sync(0xffffffffu, __float_as_uint(fb));
+                    if (lane == 0 && sp < BVH_STACK) {
+                        s_ref[warp][sp] = left_first ? right : left;
+                        s_bound[warp][sp] = __uint_as_float(fmin);
+                    }
+                    if (sp < BVH_STACK) ++sp;
+                    if (COUNT) ++c_push;
+                    __syncwarp();
+                    cur = left_first ? left : right;
+                    continue;
+                }
+                if (ml != 0u) { cur = left; continue; }
+                if (mr != 0u) { cur = right; continue; }
+            }
+            // pop the next parked subtree that some lane can still use
+            bool found = false;
+            while (sp > 0) {
+                --sp;
+                const float pb = s_bound[warp][sp];
+                const int pr = s_ref[warp][sp];
+                if (__ballot_sync(0xffffffffu, active && !(pb * BVH_SHRINK > best_d)) != 0u) {
+                    cur = pr; found = true; break;
+                }
+            }
+            __syncwarp();
+            if (!found) break;
+        }
+    }
+    if (active) keys[t] = best;
+    if (COUNT && lane == 0) {
+        atomicAdd(&g_bvh_counters[0], (unsigned long long)c_inner);
+        atomicAdd(&g_bvh_counters[1], (unsigned long long)c_leaf);
+        atomicAdd(&g_bvh_counters[2], (unsigned long long)c_push);
+        atomicAdd(&g_bvh_counters[3], 1ull);
+    }
+    if (FUSED) {
+        // K3 + K4 for this thread's query (functions/general.py:299-306, :160-181)
+        double acc[MOM];
+#pragma unroll
+        for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
+        if (active && best != KEY_NONE) {
+            float wqx, wqy, wqz, w1x, w1y, w1z;
+            s1_matvec(st->mw_base, x, y, z, wqx, wqy, wqz);
+            s1_matvec(st->mw_base, wx, wy, wz, w1x, w1y, w1z);
+            const double dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+            if (dist < thresh) {
+                float bx, by, bz;
+                s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);
+                moments_add(acc, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2]);
+            }
+        }
+        block_reduce_moments<PKT_THREADS>(acc, partials);
     }
 }
 

@@ -25,24 +25,26 @@ def time_nn(e, reps=5):
 m = int(os.environ.get("M", 1_000_000)); n = int(os.environ.get("N", 1_000_000))
 cfg = meshgen.config_cloud(m, n, 200, 201)
 aligned = meshgen.bunny_like(m, 201, noise=1e-3)       # same samples without the rigid offset
-for name, mov in (("offset/random", cfg["moving"]), ("offset/morton", cfg["moving"][morton_order(cfg["moving"])]),
-                  ("aligned/random", aligned), ("aligned/morton", aligned[morton_order(aligned)])):
-    with IcpEngine(nn_mode=1) as e:
-        e.set_base(cfg["base"]); e.set_moving(mov); e.set_matrices(np.eye(4), np.eye(4))
-        print(json.dumps(dict(case=name, m=m, n=n, ms=time_nn(e))), flush=True)
+for variant in (10, 0):
+    for name, mov in (("offset", cfg["moving"]), ("aligned", aligned)):
+        with IcpEngine(nn_mode=1, nn_variant=variant) as e:
+            e.set_base(cfg["base"]); e.set_moving(mov); e.set_matrices(np.eye(4), np.eye(4))
+            print(json.dumps(dict(case=name, kernel="per-thread" if variant == 10 else "packet", m=m, n=n, warm_ms=time_nn(e))), flush=True)
 import ctypes
 for name, mov in (("offset", cfg["moving"]), ("aligned", aligned)):
-    with IcpEngine(nn_mode=1, nn_variant=99) as e:
+  for cv in (99, 98):
+    with IcpEngine(nn_mode=1, nn_variant=cv) as e:
         e.set_base(cfg["base"]); e.set_moving(mov); e.set_matrices(np.eye(4), np.eye(4))
         buf = (ctypes.c_uint64 * 4)()
         e._lib.icp_debug_counters(e._h, buf, 1)
         e.nn()
         e._lib.icp_debug_counters(e._h, buf, 1)
-        print(json.dumps(dict(case=name, inner_per_q=buf[0] / buf[3], leaf_per_q=buf[1] / buf[3], push_per_q=buf[2] / buf[3])), flush=True)
-with IcpEngine(nn_mode=1, use_target=False) as e:
+        print(json.dumps(dict(case=name, kernel="per-thread" if cv == 99 else "packet(per warp)", inner=buf[0] / buf[3], leaf=buf[1] / buf[3], push=buf[2] / buf[3])), flush=True)
+for variant in (10, 0):
+  with IcpEngine(nn_mode=1, use_target=False, nn_variant=variant) as e:
     e.set_base(cfg["base"]); e.set_moving(cfg["moving"]); e.set_matrices(np.eye(4), np.eye(4))
     e.run(2); e.set_matrices(np.eye(4), np.eye(4)); e.reset_convergence()
     per = []
     for i in range(30):
         e.run(1); per.append(round(e.last_elapsed_ms(), 3))
-    print(json.dumps(dict(per_iter_ms=per)))
+    print(json.dumps(dict(variant=variant, per_iter_ms=per)))
