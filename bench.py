@@ -37,6 +37,7 @@ WORKLOADS = {
     "c2": (100_000, 100_000, 100, 101, "C2: 100k moving vs 100k base bunny-like clouds"),
     "c3": (1_000_000, 1_000_000, 200, 201, "C3: 1M moving vs 1M base bunny-like clouds"),
     "c4": (1_000_000, 10_000_000, 300, 301, "C4: 1M moving vs 10M base, base sharded across ranks"),
+    "c5": (5_000_000, 5_000_000, 500, 501, "C5: 5M vs 5M, 25% outliers, reject_fraction 0.25, icp_include mask"),
 }
 
 
@@ -45,6 +46,12 @@ def make_workload(name):
 
     if name == "c1":
         return meshgen.config_c1()
+    if name == "c5":
+        from object_alignment_b200 import build_vlist_from_arrays
+
+        cfg = meshgen.config_c5(WORKLOADS[name][0], "include")
+        cfg["vlist"] = build_vlist_from_arrays(cfg["moving"].shape[0], cfg["groups"])   # icp_align.py:56-80
+        return cfg
     m, n, sb, sm, _ = WORKLOADS[name]
     return meshgen.config_cloud(m, n, sb, sm)
 
@@ -220,16 +227,18 @@ def run_ours(args, rank, world, local_rank):
     ident = np.eye(4, dtype=np.float32)
 
     nn_mode = 1 if args.nn_mode == "bvh" else 0
+    vlist = cfg.get("vlist")
+    m_eff = int(vlist.shape[0]) if vlist is not None else m
     eng = IcpEngine(thresh=cfg["thresh"], use_target=False, align_meth="0", stride=1,
                     device=local_rank, rank=rank, world_size=world, nn_variant=args.nn_variant,
-                    nn_mode=nn_mode)
+                    nn_mode=nn_mode, reject_fraction=cfg.get("reject_fraction", 0.0))
     t0 = time.perf_counter()
     eng.set_base_sharded(base)
     base_upload_s = time.perf_counter() - t0
     icpdist.connect_engine(eng, dist)
     pinned = PinnedArray(mov.shape, np.float32)
     pinned.array[...] = mov
-    eng.set_moving(pinned.array)
+    eng.set_moving(pinned.array, vlist)
     eng.set_matrices(ident, ident)
 
     def barrier():
@@ -274,12 +283,12 @@ def run_ours(args, rank, world, local_rank):
     eng.reset_convergence()
     pose = ident.copy()
     for _ in range(min(args.warmup, 2)):
-        eng.set_moving(pinned.array); eng.set_matrices(pose, ident); eng.step()
+        eng.set_moving(pinned.array, vlist); eng.set_matrices(pose, ident); eng.step()
     pose = ident.copy()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.set_moving(pinned.array)            # H2D of this step's inputs from pinned memory
+        eng.set_moving(pinned.array, vlist)     # H2D of this step's inputs from pinned memory
         eng.set_matrices(pose, ident)
         M, st = eng.step()                      # D2H: the fp64 4x4 + the stats record
         pose = eng.matrix_world()               # D2H: the updated matrix_world
@@ -287,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     if dist is not None:
         e2e_s = icpdist.allreduce_max_scalar(e2e_s, dist)
-    h2d = mov.nbytes + 2 * 64
+    h2d = mov.nbytes + 2 * 64 + (vlist.nbytes if vlist is not None else 0)
     d2h = 16 * 8 + 168 + 64
 
     if rank != 0:
@@ -304,6 +313,7 @@ def run_ours(args, rank, world, local_rank):
         pass
     n_local = n // world
     nn_avg_ms = nn_ms / max(nn_launches, 1)
+    m_all, m = m, m_eff                                        # work is counted on the sampled queries
     flops = 8.0 * m * n_local                                  # 8 FLOP per (query, base) pair
     achieved = flops / (nn_avg_ms * 1e-3) / 1e12
     traffic = None
@@ -343,8 +353,9 @@ def run_ours(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][4], "n_moving": m, "n_base": n,
-                   "base_shards": world, "thresh": cfg["thresh"], "sample_fraction": 1.0,
+        "config": {"workload": WORKLOADS[args.workload][4], "n_moving": m_all, "m_eff": m, "n_base": n,
+                   "reject_fraction": cfg.get("reject_fraction", 0.0), "base_shards": world,
+                   "thresh": cfg["thresh"] if np.isfinite(cfg["thresh"]) else "inf", "sample_fraction": 1.0,
                    "align_meth": "RIGID", "nn_mode": args.nn_mode, "nn_variant": args.nn_variant,
                    "l2": "flushed between timed steps (256 MB memset)",
                    "collectives": "ncclAllReduce MIN u64[M] + SUM f64[20] per step" if world > 1 else "none"},
@@ -363,12 +374,12 @@ def run_ours(args, rank, world, local_rank):
         "final_pose_row0": [float(x) for x in final_pose[0]],
     }
     eng.close()
-    if world == 1 and not args.no_secondary:
+    if world == 1 and not args.no_secondary and vlist is None and not cfg.get("reject_fraction"):
         other = 0 if nn_mode == 1 else 1
         line["next_rows" if other == 1 else "north_star_kernel"] = {
             ("N2_bvh_search" if other == 1 else "bruteforce"): measure_secondary(
                 cfg, local_rank, other, args.steps if other == 1 else min(args.steps, 5), 3)}
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and vlist is None:
         line["cpu_baseline"] = cpu_baseline(cfg, args.cpu_sample, 2)
         line["cpu_fair"] = cpu_fair_comparator(cfg)
     print(json.dumps(line), flush=True)

@@ -636,6 +636,8 @@ struct icp_handle {
     uint32_t* d_slot_pos = nullptr;
     uint32_t* d_pos_slot = nullptr;
     float4* d_mov_slots = nullptr;         // moving vertices gathered into slot order (fused kernel input)
+    void* d_order_scratch = nullptr;
+    size_t order_scratch_bytes = 0;
     long long order_capacity = 0;
     bool order_valid = false;
     int order_stride = 0;
@@ -908,30 +910,37 @@ int ensure_query_order(icp_handle* h, long long n_q)
         h->order_capacity = cap;
     }
     if (n_q > 0) {
-        unsigned long long *codes = nullptr, *codes_out = nullptr;
-        uint32_t* pos = nullptr;
-        float *part = nullptr, *bbox = nullptr;
-        void* temp = nullptr;
-        size_t temp_bytes = 0;
+        // one grow-only scratch buffer, carved up; everything is stream-ordered (no host sync)
         const int* vl = h->has_vlist ? h->d_vlist : nullptr;
         const int pb = (int)std::min<long long>((n_q + 255) / 256, (long long)h->sm_count * 4);
-        CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n_q * 8));
-        CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n_q * 8));
-        CUDA_TRY(h, cudaMalloc((void**)&pos, (size_t)n_q * 4));
-        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 6 * 4));
-        CUDA_TRY(h, cudaMalloc((void**)&bbox, 6 * 4));
+        size_t temp_bytes = 0;
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr,
+                                                    (unsigned long long*)nullptr, (uint32_t*)nullptr,
+                                                    (uint32_t*)nullptr, (int)n_q, 0, 63, h->stream));
+        auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+        const size_t o_codes = 0, o_codes_out = o_codes + up((size_t)n_q * 8), o_pos = o_codes_out + up((size_t)n_q * 8),
+                     o_part = o_pos + up((size_t)n_q * 4), o_bbox = o_part + up((size_t)pb * 24), o_temp = o_bbox + 256,
+                     total = o_temp + up(temp_bytes);
+        if (total > h->order_scratch_bytes) {
+            if (h->d_order_scratch) cudaFree(h->d_order_scratch);
+            h->d_order_scratch = nullptr; h->order_scratch_bytes = 0;
+            CUDA_TRY(h, cudaMalloc(&h->d_order_scratch, total));
+            h->order_scratch_bytes = total;
+        }
+        char* sb = (char*)h->d_order_scratch;
+        unsigned long long* codes = (unsigned long long*)(sb + o_codes);
+        unsigned long long* codes_out = (unsigned long long*)(sb + o_codes_out);
+        uint32_t* pos = (uint32_t*)(sb + o_pos);
+        float* part = (float*)(sb + o_part);
+        float* bbox = (float*)(sb + o_bbox);
         k_query_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_mov, vl, stride, n_q, part);
         k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
         k_query_codes<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_mov, vl, stride, n_q, bbox, codes, pos);
-        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, pos, h->d_slot_pos, (int)n_q, 0, 63, h->stream));
-        CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
-        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, pos, h->d_slot_pos, (int)n_q, 0, 63, h->stream));
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(sb + o_temp, temp_bytes, codes, codes_out, pos, h->d_slot_pos, (int)n_q, 0, 63, h->stream));
         k_invert_permutation<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_slot_pos, n_q, h->d_pos_slot);
         k_gather_mov_slots<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_mov, vl, stride, h->d_slot_pos, n_q, h->d_mov_slots);
         h->launches += 6;
         CUDA_TRY(h, cudaGetLastError());
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        cudaFree(codes); cudaFree(codes_out); cudaFree(pos); cudaFree(part); cudaFree(bbox); cudaFree(temp);
     }
     h->order_valid = true;
     h->order_stride = stride;
@@ -1230,7 +1239,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
