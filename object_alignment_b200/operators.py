@@ -162,3 +162,113 @@ class OBJECT_OT_icp_align(Operator):
             print('Avg last 5 rotation angle: %f' % np.mean([r.angle for r in recs[-5:]]))
         print('Aligned obj in %f sec' % (time.time() - start))
         return {'FINISHED'}
+
+
+class OBJECT_OT_icp_align_feedback(Operator):
+    """Uses ICP alignment to iteratively align two objects and redraws every n iterations (GPU engine)"""
+    # Row N3 of SURVEY.md section 8f: the modal variant (reference operators/icp_align_feedback.py:31-304).
+    # Same engine handle for the whole run; every TIMER tick runs `redraw_frequency` iterations
+    # device-resident (icp_run) and writes matrix_world back once, so the viewport shows progress.
+    # Two reference bugs are fixed knowingly: `take_m_with` is an unqualified name in iterate()
+    # (icp_align_feedback.py:267, NameError) and the loop test `total_iters <= iters` (:113) runs one
+    # iteration too many; here exactly `icp_iterations` iterations run, like the non-modal operator.
+    bl_idname = "object.align_icp_redraw"
+    bl_label = "ICP Align Redraw"
+    bl_options = {'REGISTER', 'UNDO'}
+
+    device = 0
+    reject_fraction = 0.0
+    _timer = None
+
+    @classmethod
+    def poll(cls, context):
+        condition_1 = len(context.selected_objects) == 2
+        condition_2 = context.object and context.object.type == 'MESH'
+        return bool(condition_1 and condition_2)
+
+    def invoke(self, context, event):
+        wm = context.window_manager
+        self._timer = wm.event_timer_add(time_step=0.01, window=context.window)   # :49
+        wm.modal_handler_add(self)
+        settings = get_addon_preferences()
+        self.start = time.time()
+        self.align_obj = context.object
+        self.base_obj = [obj for obj in context.selected_objects if obj != self.align_obj][0]
+        self.align_obj.rotation_mode = 'QUATERNION'
+        self.vlist = build_vlist(self.align_obj)
+        self.iters = settings.icp_iterations
+        self.redraw_frequency = settings.redraw_frequency
+        self.take_m_with = settings.take_m_with
+        self.use_target = settings.use_target
+        thresh = settings.min_start
+        if not thresh > 0:
+            raise TypeError("cannot unpack non-iterable NoneType object")
+        self.base_nn = VertexNN.FromObject(
+            self.base_obj, context.evaluated_depsgraph_get(), device=self.device, thresh=thresh,
+            target_d=settings.target_d, use_target=settings.use_target, align_meth=settings.align_meth,
+            stride=stride_from_sample_fraction(settings.sample_fraction),
+            reject_fraction=self.reject_fraction)
+        eng = self.base_nn.engine
+        eng.set_moving(extract_coords(self.align_obj), self.vlist)
+        eng.set_matrices(matrix_to_array(self.align_obj.matrix_world),
+                         matrix_to_array(self.base_obj.matrix_world))
+        self.total_iters = 0
+        self.converged = False
+        self.records = []
+        return {'RUNNING_MODAL'}
+
+    def modal(self, context, event):
+        if event.type in {'RIGHTMOUSE', 'ESC'}:
+            return self.cancel(context)
+        if event.type == 'TIMER':
+            context.area.tag_redraw()
+            if self.total_iters < self.iters and not self.converged:
+                self.iterate(context, min(self.redraw_frequency, self.iters - self.total_iters))
+                if self.total_iters < self.iters and not self.converged:
+                    return {'RUNNING_MODAL'}
+            return self.finish(context)
+        return {'PASS_THROUGH'}
+
+    def iterate(self, context, count=1):
+        """`count` loop bodies of icp_align_feedback.py:250-288 in one device-resident batch."""
+        eng = self.base_nn.engine
+        try:
+            done, converged, recs = eng.run(count)
+        except IcpError as e:
+            self._release(context)
+            if e.code == N.ICP_ERR_TOO_FEW_PAIRS:
+                raise ValueError("input arrays are of wrong shape or type") from None
+            raise
+        self.align_obj.matrix_world = array_to_matrix_like(eng.matrix_world(), self.align_obj.matrix_world)
+        if self.take_m_with:
+            _apply_to_m_objects(context, [r.M.astype(np.float32) for r in recs])
+        self.align_obj.update_tag()
+        self.total_iters += done
+        self.converged = converged
+        self.records.extend(recs)
+        if converged and recs:
+            print('Converged in %s iterations' % str(self.total_iters))
+            print('Final Translation: %f ' % recs[-1].trans)
+            print('Final Avg Dist: %f' % recs[-1].mean_dist)
+            print('Final St Dev %f' % recs[-1].std_dist)
+
+    def _release(self, context):
+        if self._timer is not None:
+            context.window_manager.event_timer_remove(self._timer)
+            self._timer = None
+        if getattr(self, "base_nn", None) is not None:
+            self.base_nn.close()
+            self.base_nn = None
+
+    def finish(self, context):
+        self._release(context)
+        if self.use_target and not self.converged and self.records:
+            print('Maxed out iterations')
+            print('Final Avg Dist: %f' % self.records[-1].mean_dist)
+            print('Final St Dev %f' % self.records[-1].std_dist)
+        print('Aligned obj in %f sec' % (time.time() - self.start))
+        return {'FINISHED'}
+
+    def cancel(self, context):
+        self._release(context)
+        return {'CANCELLED'}

@@ -378,13 +378,44 @@ class _ViewLayer:
         self.updates += 1
 
 
+class _WindowManager:
+    def __init__(self):
+        self.timers, self.handlers = [], []
+
+    def event_timer_add(self, time_step=0.01, window=None):
+        self.timers.append(time_step)
+        return len(self.timers)
+
+    def event_timer_remove(self, timer):
+        self.timers.remove(self.timers[timer - 1]) if self.timers else None
+
+    def modal_handler_add(self, op):
+        self.handlers.append(op)
+
+
+class _Area:
+    def __init__(self):
+        self.redraws = 0
+
+    def tag_redraw(self):
+        self.redraws += 1
+
+
+class Event:
+    def __init__(self, type_):
+        self.type = type_
+
+
 class Context:
-    """Duck-typed ``bpy.context`` (icp_align.py:43-53,133)."""
+    """Duck-typed ``bpy.context`` (icp_align.py:43-53,133; icp_align_feedback.py:47-49,110)."""
 
     def __init__(self, active, selected):
         self.object = active
         self.selected_objects = list(selected)
         self.view_layer = _ViewLayer()
+        self.window_manager = _WindowManager()
+        self.window = None
+        self.area = _Area()
 
     def evaluated_depsgraph_get(self):
         return None

@@ -304,8 +304,11 @@ def test_affine_matrix_from_points_kat_and_errors():
 
 
 # ------------------------------------------------------------------ the operator, end to end
+@pytest.mark.parametrize("nn_mode", [0, 1])
 @pytest.mark.parametrize("name", scenario_names())
-def test_operator_execute_matches_reference_golden(name):
+def test_operator_execute_matches_reference_golden(name, nn_mode, monkeypatch):
+    from object_alignment_b200 import functions as oab_functions
+    monkeypatch.setattr(oab_functions, "DEFAULT_NN_MODE", nn_mode)
     g = Golden(name)
     align, base = _objects(g)
     oab.set_addon_preferences(oab.IcpPreferences(**g.prefs))
@@ -396,6 +399,38 @@ def test_reference_shaped_loop_with_icp_step():
         assert st.pairs == 1002
     finally:
         nn.close()
+
+
+@pytest.mark.parametrize("name", ["c1_fixed20", "c1_defaults", "c1_include"])
+def test_modal_operator_matches_reference_golden(name):
+    """Row N3: the timer-driven operator reaches the same pose in the same number of iterations."""
+    g = Golden(name)
+    align, base = _objects(g)
+    prefs = dict(g.prefs, redraw_frequency=3)
+    oab.set_addon_preferences(oab.IcpPreferences(**prefs))
+    ctx = ms.Context(align, [align, base])
+    op = oab.OBJECT_OT_icp_align_feedback()
+    assert op.poll(ctx)
+    assert op.invoke(ctx, ms.Event("NONE")) == {"RUNNING_MODAL"}
+    assert op.modal(ctx, ms.Event("MOUSEMOVE")) == {"PASS_THROUGH"}
+    ticks = 0
+    while True:
+        ticks += 1
+        r = op.modal(ctx, ms.Event("TIMER"))
+        if r != {"RUNNING_MODAL"}:
+            break
+        assert ticks < 100
+    assert r == {"FINISHED"}
+    assert op.total_iters == g.iterations and op.converged == g.converged
+    assert ctx.area.redraws == ticks and ctx.window_manager.timers == []
+    np.testing.assert_allclose(align.matrix_world.a, g.matrix_world, rtol=0, atol=1e-5)
+    # ESC cancels and releases the engine
+    align2, base2 = _objects(g)
+    ctx2 = ms.Context(align2, [align2, base2])
+    op2 = oab.OBJECT_OT_icp_align_feedback()
+    op2.invoke(ctx2, ms.Event("NONE"))
+    op2.modal(ctx2, ms.Event("TIMER"))
+    assert op2.modal(ctx2, ms.Event("ESC")) == {"CANCELLED"} and op2.base_nn is None
 
 
 # ------------------------------------------------------------------ percentile rejection (new)
