@@ -324,7 +324,8 @@ def run_ours(args, rank, world, local_rank):
     if nn_mode == 1:
         line_roofline = bvh_roofline(m, n_local, nn_avg_ms, hbm_peak_of(peaks), args.workload)
     roofline = line_roofline if nn_mode == 1 else {
-        "kernel": "k_nn_bruteforce", "bound": "fp32",
+        "kernel": "k_nn_bruteforce_filter<4,3>" if (args.nn_variant in (0, 20) and n_local >= 262144) else "k_nn_bruteforce",
+        "bound": "fp32",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "traffic": traffic,
         "peak_source": "FFMA/FFMA2 micro-benchmark measured in this run (icp_measure_fp32_peak); "

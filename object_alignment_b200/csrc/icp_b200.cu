@@ -627,6 +627,10 @@ struct icp_handle {
     long long n_local = 0, n_global = 0, base_off = 0;
     int n_tiles = 0;
     bool have_base = false;
+    // expansion-form filter tiles for the brute-force kernel (nn_variant 20..), built lazily
+    float* d_filter_tiles = nullptr;
+    FilterInfo* d_filter_info = nullptr;
+    bool filter_built = false;
     // spatial index (nn_mode == ICP_NN_BVH), built lazily from d_base4
     BvhNode* d_bvh_nodes = nullptr;
     float4* d_bvh_sorted = nullptr;
@@ -795,11 +799,82 @@ int launch_nn_t(icp_handle* h, long long n_q)
     return ICP_OK;
 }
 
+int build_filter(icp_handle* h)
+{
+    if (h->filter_built) return ICP_OK;
+    if (h->d_filter_tiles) { cudaFree(h->d_filter_tiles); h->d_filter_tiles = nullptr; }
+    if (!h->d_filter_info) CUDA_TRY(h, cudaMalloc((void**)&h->d_filter_info, sizeof(FilterInfo)));
+    const long long n = h->n_local, n_pad = (long long)h->n_tiles * NN_TILE;
+    if (n > 0) {
+        float *part = nullptr, *bbox = nullptr;
+        const int pb = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
+        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 24));
+        CUDA_TRY(h, cudaMalloc((void**)&bbox, 24));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_filter_tiles, (size_t)n_pad * 4 * sizeof(float)));
+        k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
+        k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+        k_filter_info<<<1, 32, 0, h->stream>>>(bbox, h->d_filter_info);
+        k_build_filter_tiles<<<(unsigned)((n_pad + 255) / 256), 256, 0, h->stream>>>(h->d_base4, n, n_pad, h->d_filter_info, h->d_filter_tiles);
+        h->launches += 4;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(part); cudaFree(bbox);
+    }
+    h->filter_built = true;
+    return ICP_OK;
+}
+
+template <int R, int STAGES>
+int launch_nn_filter_t(icp_handle* h, long long n_q)
+{
+    int rc = build_filter(h);
+    if (rc) return rc;
+    auto kern = k_nn_bruteforce_filter<R, STAGES>;
+    const size_t smem = (size_t)STAGES * NNF_TILE_BYTES + STAGES * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)h->sm_count * occ;
+    long long want_y = (8 * slots + qb - 1) / qb;
+    long long max_y = std::max<long long>(1, h->n_tiles / 8);
+    long long gy = std::max<long long>(1, std::min(want_y, max_y));
+    int tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy);
+    gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    if (gy > 65535) { gy = 65535; tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy); gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta; }
+    dim3 grid((unsigned)qb, (unsigned)gy);
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_filter_tiles, h->d_base_tiles, h->d_filter_info, h->n_tiles,
+                                                tiles_per_cta, qx, qy, qz, n_q, h->d_keys, (uint32_t)h->base_off,
+                                                &h->d_state->converged);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
 int launch_nn(icp_handle* h, long long n_q)
 {
     if (n_q <= 0 || h->n_tiles <= 0) return ICP_OK;
+    // default (variant 0): the expansion-filter kernel once every CTA scans enough chunks for its
+    // slow path to be rare (>= 256 tiles = 262k base vertices per shard), the direct kernel below
+    int variant = h->prm.nn_variant;
+    if (variant == 0) variant = (h->n_tiles >= 256) ? 20 : 2;
+    if (variant >= 20 && variant <= 29) {
+        int rc = build_filter(h);      // outside the profiled region (one-time)
+        if (rc) return rc;
+    }
     ProfScope ps(h, 0);
-    switch (h->prm.nn_variant) {
+    switch (variant) {
+        case 20: return launch_nn_filter_t<4, 3>(h, n_q);   // expansion filter + exact re-check
+        case 21: return launch_nn_filter_t<8, 3>(h, n_q);
+        case 22: return launch_nn_filter_t<4, 4>(h, n_q);
+        case 23: return launch_nn_filter_t<6, 3>(h, n_q);
+        case 24: return launch_nn_filter_t<2, 3>(h, n_q);
         case 1: return launch_nn_t<4, 4, false>(h, n_q);   // scalar pipe, 4 queries / thread
         case 2: return launch_nn_t<4, 4, true>(h, n_q);    // packed f32x2
         case 3: return launch_nn_t<8, 4, true>(h, n_q);
@@ -1239,7 +1314,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1273,6 +1348,7 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
     const long long n_pad = (long long)h->n_tiles * NN_TILE;
     h->n_local = n_local; h->n_global = n_global; h->base_off = global_offset;
     h->bvh_built = false;
+    h->filter_built = false;
     h->warm_valid = false;
     if (n_local > 0) {
         float* d_raw = nullptr;

@@ -17,7 +17,7 @@ from tests.golden_util import GOLDEN, Golden, scenario_names
 
 pytestmark = pytest.mark.gpu
 
-NN_VARIANTS = [0, 1, 2, 3, 4, 5, 6]
+NN_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 20, 21, 22, 23, 24]
 
 
 def _rand_cloud(n, seed, scale=1.0):
@@ -92,6 +92,44 @@ def test_nn_vlist_stride_and_matrices():
         assert idx.shape == res["idx"].shape
         assert np.array_equal(idx, res["idx"])
         assert np.array_equal(d2.view(np.uint32), res["d2"].view(np.uint32))
+
+
+@pytest.mark.parametrize("variant", [20, 21])
+@pytest.mark.parametrize("case", ["surface", "far_outliers", "duplicates", "collinear", "volume", "lattice",
+                                  "far_from_origin", "sorted_base"])
+def test_filter_kernel_matches_oracle(case, variant):
+    """The expansion-form filter variant of K2 must return the same keys as the exact metric:
+    near-ties, exact ties, coherent base order (many running-min improvements) and data far from
+    the origin (where the expansion cancels worst) included."""
+    if case == "far_from_origin":
+        base = (_rand_cloud(30_000, 81) * 0.5 + np.array([800.0, -500.0, 300.0], np.float32)).astype(np.float32)
+        mov = (_rand_cloud(9_000, 82) * 0.5 + np.array([800.0, -500.0, 300.0], np.float32)).astype(np.float32)
+    elif case == "sorted_base":
+        cfg = meshgen.config_cloud(10_000, 40_000, 83, 84)
+        base = cfg["base"][np.lexsort(cfg["base"].T)]
+        mov = cfg["moving"]
+    else:
+        base, mov = _clouds_for_bvh(case)
+    with IcpEngine(nn_variant=variant) as e:
+        e.set_base(base)
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+    oi, od = orc.nn_bruteforce(mov, base)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+
+
+def test_filter_kernel_equals_direct_kernel_at_1m():
+    cfg = meshgen.config_cloud(1_000_000, 1_000_000, 200, 201)
+    res = {}
+    for variant in (0, 20):
+        with IcpEngine(nn_variant=variant) as e:
+            e.set_base(cfg["base"])
+            e.set_moving(cfg["moving"])
+            e.set_matrices(np.eye(4), np.eye(4))
+            res[variant] = e.nn()
+    assert np.array_equal(res[0][0], res[20][0]) and np.array_equal(res[0][1], res[20][1])
 
 
 def test_nn_100k_vs_100k_c2():
