@@ -43,6 +43,9 @@ typedef enum icp_nn_mode {
     ICP_NN_BRUTEFORCE = 0, /* O(M N) tiled min-search, the north-star path (general.py:297, D2) */
     ICP_NN_BVH = 1         /* exact search through an implicit BVH over Morton-sorted base vertices
                               (the "KD-tree equivalent"); bit-identical results */
+    , ICP_NN_SURFACE = 2   /* closest point on the TRIANGULATED SURFACE of the base mesh -- the reference's
+                              real BVHTree.find_nearest semantics; needs
+                              icp_set_base_triangles instead of icp_set_base */
 } icp_nn_mode;
 
 /* Parameter block; mirrors ObjectAlignmentPreferences (lib/preferences.py:31-72) as read by
@@ -93,6 +96,11 @@ int  icp_set_params(icp_handle *h, const icp_params *params); /* device/rank/wor
  * index of the shard's first vertex in the whole base, n_global the size of the whole base. */
 int  icp_set_base(icp_handle *h, const float *xyz, int64_t n_local, int64_t global_offset,
                   int64_t n_global);
+/* Surface mode: THIS rank's shard of the base mesh's triangles, as corner coordinates
+ * (n_local x 9 floats: a.xyz, b.xyz, c.xyz, base-local space; Blender's loop triangles of the
+ * evaluated mesh).  Indices reported by icp_nn are then triangle indices. */
+int  icp_set_base_triangles(icp_handle *h, const float *tri_xyz, int64_t n_local, int64_t global_offset,
+                            int64_t n_global);
 /* Moving (align) object's vertices, align-local xyz fp32 (mesh.vertices.foreach_get("co")), and
  * the vertex list produced by the include/exclude rule (icp_align.py:56-80); vlist == NULL
  * means all vertices (icp_align.py:80).  Indices must be in [0, n_vertices). */

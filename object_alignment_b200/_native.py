@@ -22,6 +22,7 @@ ICP_ERR_SINGULAR = 7
 
 NN_BRUTEFORCE = 0
 NN_BVH = 1
+NN_SURFACE = 2
 
 
 class IcpParams(C.Structure):
@@ -66,6 +67,7 @@ SIGNATURES = {
     "icp_destroy": (C.c_int, [C.c_void_p]),
     "icp_set_params": (C.c_int, [C.c_void_p, C.POINTER(IcpParams)]),
     "icp_set_base": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
+    "icp_set_base_triangles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "icp_set_moving": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "icp_set_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "icp_comm_unique_id": (C.c_int, [C.c_void_p]),

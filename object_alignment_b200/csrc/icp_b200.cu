@@ -31,6 +31,7 @@
 #include "icp_state.cuh"
 #include "nn_bruteforce.cuh"
 #include "nn_bvh.cuh"
+#include "nn_surface.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -74,7 +75,8 @@ __global__ void k_transform_queries(const DevState* __restrict__ st, const float
                                     const uint32_t* __restrict__ slot_pos,
                                     float* __restrict__ qx, float* __restrict__ qy,
                                     float* __restrict__ qz, unsigned long long* __restrict__ keys,
-                                    int warm, const float4* __restrict__ base4, long long base_off,
+                                    int warm, const float4* __restrict__ base4,
+                                    const float4* __restrict__ tris4, long long base_off,
                                     long long n_local)
 {
     if (st->converged) return;
@@ -92,8 +94,16 @@ __global__ void k_transform_queries(const DevState* __restrict__ st, const float
         const unsigned long long old = keys[t];
         const long long j = (long long)(uint32_t)(old & 0xFFFFFFFFull) - base_off;
         if (old != KEY_NONE && j >= 0 && j < n_local) {
-            const float4 b = base4[j];
-            const float d = s4_d2(x, y, z, b.x, b.y, b.z);
+            float d;
+            if (tris4) {                                   // surface mode: previous winning triangle
+                const float4 a = tris4[3 * j], b = tris4[3 * j + 1], c = tris4[3 * j + 2];
+                float rx, ry, rz;
+                closest_on_tri(x, y, z, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, rx, ry, rz);
+                d = s10_d2(x, y, z, rx, ry, rz);
+            } else {
+                const float4 b = base4[j];
+                d = s4_d2(x, y, z, b.x, b.y, b.z);
+            }
             if (d < __int_as_float(0x7f800000))
                 key = ((unsigned long long)__float_as_uint(d) << 32) | (old & 0xFFFFFFFFull);
         }
@@ -229,7 +239,8 @@ __device__ __forceinline__ PairEval eval_pair(const DevState* __restrict__ st,
                                               const float* __restrict__ qy,
                                               const float* __restrict__ qz,
                                               const unsigned long long* __restrict__ keys,
-                                              const float4* __restrict__ base4, long long base_off,
+                                              const float4* __restrict__ base4,
+                                              const float4* __restrict__ tris4, long long base_off,
                                               long long n_local, double thresh, int use_select,
                                               long long t, long long p)
 {
@@ -244,7 +255,13 @@ __device__ __forceinline__ PairEval eval_pair(const DevState* __restrict__ st,
         const unsigned long long c = (key & 0xFFFFFFFF00000000ull) | (unsigned long long)p;
         if (!st->sel_valid || c > st->sel_threshold) return e;
     }
-    const float4 co1 = base4[j];
+    float4 co1;
+    if (tris4) {       // surface mode: the target is the closest point on the winning triangle (S9)
+        const float4 a = tris4[3 * j], b = tris4[3 * j + 1], c = tris4[3 * j + 2];
+        closest_on_tri(qx[t], qy[t], qz[t], a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, co1.x, co1.y, co1.z);
+    } else {
+        co1 = base4[j];
+    }
     float wqx, wqy, wqz, w1x, w1y, w1z;
     s1_matvec(st->mw_base, qx[t], qy[t], qz[t], wqx, wqy, wqz);
     s1_matvec(st->mw_base, co1.x, co1.y, co1.z, w1x, w1y, w1z);
@@ -262,8 +279,8 @@ k_filter_moments(const DevState* __restrict__ st, const float* __restrict__ mov,
                  const int* __restrict__ vlist, int stride, long long n_q,
                  const float* __restrict__ qx, const float* __restrict__ qy,
                  const float* __restrict__ qz, const unsigned long long* __restrict__ keys,
-                 const float4* __restrict__ base4, long long base_off, long long n_local,
-                 double thresh, int use_select, const uint32_t* __restrict__ slot_pos,
+                 const float4* __restrict__ base4, const float4* __restrict__ tris4, long long base_off,
+                 long long n_local, double thresh, int use_select, const uint32_t* __restrict__ slot_pos,
                  double* __restrict__ partials)
 {
     if (st->converged) return;
@@ -274,7 +291,7 @@ k_filter_moments(const DevState* __restrict__ st, const float* __restrict__ mov,
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_q;
          t += (long long)gridDim.x * blockDim.x) {
         const long long p = slot_pos ? (long long)slot_pos[t] : t;
-        const PairEval e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off,
+        const PairEval e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, tris4, base_off,
                                      n_local, thresh, use_select, t, p);
         if (!e.keep) continue;
         moments_add(acc, e.ax, e.ay, e.az, e.bx, e.by, e.bz, e.dist, s0, s1, s2);
@@ -436,6 +453,7 @@ k_pairs_count(const DevState* __restrict__ st, const float* __restrict__ mov,
               const int* __restrict__ vlist, int stride, long long n_q, const float* __restrict__ qx,
               const float* __restrict__ qy, const float* __restrict__ qz,
               const unsigned long long* __restrict__ keys, const float4* __restrict__ base4,
+              const float4* __restrict__ tris4,
               long long base_off, long long n_local, double thresh, int use_select,
               const uint32_t* __restrict__ pos_slot,
               unsigned char* __restrict__ flags, long long* __restrict__ block_counts)
@@ -444,7 +462,7 @@ k_pairs_count(const DevState* __restrict__ st, const float* __restrict__ mov,
     bool keep = false;
     if (p < n_q) {
         const long long t = pos_slot ? (long long)pos_slot[p] : p;
-        keep = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off, n_local, thresh,
+        keep = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, tris4, base_off, n_local, thresh,
                          use_select, t, p).keep;
         flags[p] = keep ? 1 : 0;
     }
@@ -466,6 +484,7 @@ k_pairs_emit(const DevState* __restrict__ st, const float* __restrict__ mov,
              const int* __restrict__ vlist, int stride, long long n_q, const float* __restrict__ qx,
              const float* __restrict__ qy, const float* __restrict__ qz,
              const unsigned long long* __restrict__ keys, const float4* __restrict__ base4,
+             const float4* __restrict__ tris4,
              long long base_off, long long n_local, double thresh, int use_select,
              const uint32_t* __restrict__ pos_slot,
              const long long* __restrict__ block_offsets, long long K, double* __restrict__ A,
@@ -475,7 +494,7 @@ k_pairs_emit(const DevState* __restrict__ st, const float* __restrict__ mov,
     PairEval e;
     e.keep = false;
     if (p < n_q)
-        e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, base_off, n_local, thresh,
+        e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, tris4, base_off, n_local, thresh,
                       use_select, pos_slot ? (long long)pos_slot[p] : p, p);
     __shared__ int warp_counts[EMIT_THREADS / 32];
     const unsigned ballot = __ballot_sync(0xffffffffu, e.keep);
@@ -627,6 +646,13 @@ struct icp_handle {
     long long n_local = 0, n_global = 0, base_off = 0;
     int n_tiles = 0;
     bool have_base = false;
+    // surface mode (ICP_NN_SURFACE): triangles of the base mesh + their LBVH
+    bool surface = false;
+    float4* d_tris4 = nullptr;             // 3 float4 per triangle, original order
+    float4* d_tri_sorted = nullptr;        // Morton order, run-padded
+    BvhNode* d_tri_nodes = nullptr;
+    int tri_runs = 0;
+    float tri_extent = 0.0f;
     // expansion-form filter tiles for the brute-force kernel (nn_variant 20..), built lazily
     float* d_filter_tiles = nullptr;
     FilterInfo* d_filter_info = nullptr;
@@ -726,6 +752,8 @@ int ensure(icp_handle* h, T*& ptr, long long& cap, long long need)
     cap = n;
     return ICP_OK;
 }
+
+bool uses_slots(const icp_handle* h) { return h->prm.nn_mode != ICP_NN_BRUTEFORCE; }
 
 long long query_count(const icp_handle* h)
 {
@@ -1060,6 +1088,8 @@ int check_ready(icp_handle* h)
     return ICP_OK;
 }
 
+int launch_nn_surface(icp_handle* h, long long n_q);
+
 // transform + nearest neighbour (+ shard resolution + percentile select)
 int enqueue_nn(icp_handle* h, long long n_q)
 {
@@ -1067,7 +1097,7 @@ int enqueue_nn(icp_handle* h, long long n_q)
     if (rc) return rc;
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
-    const bool bvh = h->prm.nn_mode == ICP_NN_BVH;
+    const bool bvh = uses_slots(h);      // BVH and surface modes: Morton-ordered slots + warm start
     if (bvh) {
         rc = ensure_query_order(h, n_q);
         if (rc) return rc;
@@ -1081,10 +1111,14 @@ int enqueue_nn(icp_handle* h, long long n_q)
             k_transform_queries<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(
                 h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q,
                 bvh ? h->d_slot_pos : nullptr, qx, qy, qz, h->d_keys,
-                (bvh && h->warm_valid) ? 1 : 0, h->d_base4, h->base_off, h->n_local);
+                (bvh && h->warm_valid) ? 1 : 0, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off,
+                h->n_local);
         h->launches += 2;
     }
-    rc = (h->prm.nn_mode == ICP_NN_BVH) ? launch_nn_bvh(h, n_q) : launch_nn(h, n_q);
+    if (h->surface != (h->prm.nn_mode == ICP_NN_SURFACE))
+        return fail(h, ICP_ERR_STATE, "nn_mode ICP_NN_SURFACE needs icp_set_base_triangles (and the vertex modes need icp_set_base)");
+    rc = h->surface ? launch_nn_surface(h, n_q)
+                    : (h->prm.nn_mode == ICP_NN_BVH ? launch_nn_bvh(h, n_q) : launch_nn(h, n_q));
     if (rc) return rc;
     if (h->prm.world_size > 1 && n_q > 0) {
         if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
@@ -1104,6 +1138,19 @@ int enqueue_nn(icp_handle* h, long long n_q)
         }
         h->launches += 17;
     }
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+int launch_nn_surface(icp_handle* h, long long n_q)
+{
+    if (n_q <= 0 || h->n_local <= 0) return ICP_OK;
+    ProfScope ps(h, 0);
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    k_nn_surface<<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz,
+                                                                      n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent,
+                                                                      &h->d_state->converged);
+    h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return ICP_OK;
 }
@@ -1171,9 +1218,9 @@ int enqueue_iteration(icp_handle* h, long long n_q)
         ProfScope ps(h, 1);
         k_filter_moments<<<g, MOM_THREADS, 0, h->stream>>>(
             h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q, qx, qy, qz,
-            h->d_keys, h->d_base4, h->base_off, h->n_local, h->prm.thresh,
+            h->d_keys, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off, h->n_local, h->prm.thresh,
             h->prm.reject_fraction > 0 ? 1 : 0,
-            h->prm.nn_mode == ICP_NN_BVH ? h->d_slot_pos : nullptr, h->d_partials);
+            uses_slots(h) ? h->d_slot_pos : nullptr, h->d_partials);
         k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
         h->launches += 2;
     }
@@ -1314,7 +1361,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1347,6 +1394,7 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
     h->n_tiles = (int)((n_local + NN_TILE - 1) / NN_TILE);
     const long long n_pad = (long long)h->n_tiles * NN_TILE;
     h->n_local = n_local; h->n_global = n_global; h->base_off = global_offset;
+    h->surface = false;
     h->bvh_built = false;
     h->filter_built = false;
     h->warm_valid = false;
@@ -1361,6 +1409,76 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(d_raw);
+    }
+    h->have_base = true;
+    return ICP_OK;
+}
+
+int icp_set_base_triangles(icp_handle* h, const float* tri_xyz, int64_t n_local, int64_t global_offset, int64_t n_global)
+{
+    if (!h) return ICP_ERR_BAD_ARG;
+    if (n_local < 0 || global_offset < 0 || n_global < n_local || (n_local > 0 && !tri_xyz))
+        return fail(h, ICP_ERR_BAD_ARG, "icp_set_base_triangles: bad sizes");
+    if (n_global > 0xFFFFFFFELL) return fail(h, ICP_ERR_BAD_ARG, "icp_set_base_triangles: too many triangles");
+    CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    for (void* p : {(void*)h->d_tris4, (void*)h->d_tri_sorted, (void*)h->d_tri_nodes}) if (p) cudaFree(p);
+    h->d_tris4 = nullptr; h->d_tri_sorted = nullptr; h->d_tri_nodes = nullptr;
+    h->n_local = n_local; h->n_global = n_global; h->base_off = global_offset;
+    h->n_tiles = 0;
+    h->surface = true;
+    h->bvh_built = false; h->filter_built = false; h->warm_valid = false;
+    h->tri_runs = 0; h->tri_extent = 0.0f;
+    if (n_local > 0) {
+        const long long n = n_local;
+        const int n_runs = (int)((n + TRI_LEAF - 1) / TRI_LEAF);
+        const long long n_pad = (long long)n_runs * TRI_LEAF;
+        float* d_raw = nullptr; float4* cent = nullptr;
+        unsigned long long *codes = nullptr, *codes_out = nullptr, *run_keys = nullptr;
+        uint32_t *order = nullptr, *order_out = nullptr;
+        int* leaf_parent = nullptr;
+        float *part = nullptr, *bbox = nullptr;
+        void* temp = nullptr;
+        size_t temp_bytes = 0;
+        const int pb = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
+        CUDA_TRY(h, cudaMalloc((void**)&d_raw, (size_t)n * 9 * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&cent, (size_t)n * 16));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_tris4, (size_t)n * 3 * 16));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_tri_sorted, (size_t)n_pad * 3 * 16));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_tri_nodes, (size_t)std::max(1, n_runs - 1) * sizeof(BvhNode)));
+        CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&order, (size_t)n * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&order_out, (size_t)n * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&run_keys, (size_t)n_runs * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&leaf_parent, (size_t)n_runs * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 24));
+        CUDA_TRY(h, cudaMalloc((void**)&bbox, 24));
+        CUDA_TRY(h, cudaMemcpyAsync(d_raw, tri_xyz, (size_t)n * 9 * 4, cudaMemcpyHostToDevice, h->stream));
+        k_tri_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_raw, n, h->d_tris4, cent);
+        // bounding box over all triangle CORNERS (3n float4, stride 1) -> Morton grid + coordinate extent
+        k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_tris4, 3 * n, part);
+        k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+        k_morton_codes<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(cent, n, bbox, codes, order);
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
+        CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
+        k_tri_gather<<<(unsigned)((n_pad + 255) / 256), 256, 0, h->stream>>>(h->d_tris4, order_out, n, n_pad, h->d_tri_sorted);
+        k_run_keys_stride<<<(unsigned)((n_runs + 255) / 256), 256, 0, h->stream>>>(codes_out, n_runs, TRI_LEAF, run_keys);
+        if (n_runs > 1) {
+            k_lbvh_topology<<<(unsigned)((n_runs + 127) / 128), 128, 0, h->stream>>>(run_keys, n_runs, h->d_tri_nodes, leaf_parent);
+            k_lbvh_fit_tris<<<(unsigned)((n_runs + 127) / 128), 128, 0, h->stream>>>(h->d_tri_sorted, n, n_runs, h->d_tri_nodes, leaf_parent);
+        }
+        float hb[6];
+        CUDA_TRY(h, cudaMemcpyAsync(hb, bbox, 24, cudaMemcpyDeviceToHost, h->stream));
+        h->launches += 8;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ext = 0.0f;
+        for (int k = 0; k < 6; ++k) ext = std::max(ext, std::fabs(hb[k]));
+        h->tri_extent = ext;
+        h->tri_runs = n_runs;
+        for (void* p : {(void*)d_raw, (void*)cent, (void*)codes, (void*)codes_out, (void*)order, (void*)order_out,
+                        (void*)run_keys, (void*)leaf_parent, (void*)part, (void*)bbox, temp}) cudaFree(p);
     }
     h->have_base = true;
     return ICP_OK;
@@ -1459,7 +1577,7 @@ int icp_nn(icp_handle* h, int32_t* idx, float* d2)
         int* d_idx = nullptr; float* d_d2 = nullptr;
         if (idx) CUDA_TRY(h, cudaMalloc((void**)&d_idx, (size_t)n_q * sizeof(int)));
         if (d2) CUDA_TRY(h, cudaMalloc((void**)&d_d2, (size_t)n_q * sizeof(float)));
-        k_unpack_keys<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_keys, h->prm.nn_mode == ICP_NN_BVH ? h->d_pos_slot : nullptr, n_q, d_idx, d_d2);
+        k_unpack_keys<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_keys, uses_slots(h) ? h->d_pos_slot : nullptr, n_q, d_idx, d_d2);
         h->launches++;
         if (idx) CUDA_TRY(h, cudaMemcpyAsync(idx, d_idx, (size_t)n_q * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         if (d2) CUDA_TRY(h, cudaMemcpyAsync(d2, d_d2, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1503,9 +1621,9 @@ int icp_make_pairs(icp_handle* h, int calc_stats, double* A, double* B, int64_t 
     const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
     const int* vl = h->has_vlist ? h->d_vlist : nullptr;
     const int use_sel = h->prm.reject_fraction > 0 ? 1 : 0;
-    const uint32_t* pos_slot = h->prm.nn_mode == ICP_NN_BVH ? h->d_pos_slot : nullptr;
+    const uint32_t* pos_slot = uses_slots(h) ? h->d_pos_slot : nullptr;
     k_pairs_count<<<nb, EMIT_THREADS, 0, h->stream>>>(h->d_state, h->d_mov, vl, stride, n_q, qx, qy, qz,
-                                                      h->d_keys, h->d_base4, h->base_off, h->n_local,
+                                                      h->d_keys, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off, h->n_local,
                                                       h->prm.thresh, use_sel, pos_slot, h->d_flags, h->d_block_counts);
     k_scan_counts<<<1, 32, 0, h->stream>>>(h->d_block_counts, nb, h->d_total);
     h->launches += 2;
@@ -1526,7 +1644,7 @@ int icp_make_pairs(icp_handle* h, int calc_stats, double* A, double* B, int64_t 
         if (rc) return rc;
         double* dA = h->d_pairs; double* dB = dA + 3 * K; double* dD = dB + 3 * K; double* dS = dD + K;
         k_pairs_emit<<<nb, EMIT_THREADS, 0, h->stream>>>(h->d_state, h->d_mov, vl, stride, n_q, qx, qy, qz,
-                                                         h->d_keys, h->d_base4, h->base_off, h->n_local,
+                                                         h->d_keys, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off, h->n_local,
                                                          h->prm.thresh, use_sel, pos_slot, h->d_block_counts, K, dA, dB, dD);
         h->launches++;
         // A, B have row stride K on the device; the caller's have row stride `capacity`

@@ -135,6 +135,13 @@ __global__ void k_run_keys(const unsigned long long* __restrict__ sorted_codes, 
     run_keys[r] = sorted_codes[(long long)r * BVH_LEAF];
 }
 
+__global__ void k_run_keys_stride(const unsigned long long* __restrict__ sorted_codes, int n_runs, int run,
+                                  unsigned long long* __restrict__ run_keys)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_runs) run_keys[r] = sorted_codes[(long long)r * run];
+}
+
 __device__ __forceinline__ int lbvh_delta(const unsigned long long* __restrict__ k, int n, int i, int j)
 {
     if (j < 0 || j >= n) return -1;

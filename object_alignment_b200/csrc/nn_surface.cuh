@@ -1,0 +1,226 @@
+// nn_surface.cuh -- row N1 of SURVEY.md section 8f: closest point on the TRIANGULATED SURFACE of the
+// base mesh, i.e. what the reference really queries: BVHTree.FromObject(base_obj, depsgraph)
+// (operators/icp_align.py:53) + base_bvh.find_nearest(co_find) (functions/general.py:297).
+//
+// Blender's C BVH is absent from /root/reference; the arithmetic restated here is Blender 3.2's
+// closest_on_tri_to_point_v3 (Ericson's region walk, all fp32, no fused multiply-adds) and
+// len_squared_v3v3 -- rules S9 / S10 of DESIGN.md, shared bit for bit with oracle/nn_oracle.c.
+// Ties between triangles go to the lowest triangle index (Blender's own tie-break depends on its
+// tree layout and is not reproducible).
+//
+// Index: the same LBVH as nn_bvh.cuh, over runs of TRI_LEAF triangles sorted by the Morton code of
+// their centroids; boxes are the triangles' bounds.  The walk prunes with the same strict,
+// 2e-6-shrunk lower bound, so the winner is exact under S9/S10.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_math.cuh"
+#include "nn_bvh.cuh"
+
+namespace icp {
+
+constexpr int TRI_LEAF = 4;
+
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
+// S9: closest point on triangle (a, b, c) to p
+__device__ __forceinline__ void closest_on_tri(float px, float py, float pz, float ax, float ay, float az,
+                                               float bx, float by, float bz, float cx, float cy, float cz,
+                                               float& rx, float& ry, float& rz)
+{
+    float abx = __fsub_rn(bx, ax), aby = __fsub_rn(by, ay), abz = __fsub_rn(bz, az);
+    float acx = __fsub_rn(cx, ax), acy = __fsub_rn(cy, ay), acz = __fsub_rn(cz, az);
+    const float apx = __fsub_rn(px, ax), apy = __fsub_rn(py, ay), apz = __fsub_rn(pz, az);
+    const float d1 = dot3_rn(abx, aby, abz, apx, apy, apz);
+    const float d2 = dot3_rn(acx, acy, acz, apx, apy, apz);
+    if (d1 <= 0.0f && d2 <= 0.0f) { rx = ax; ry = ay; rz = az; return; }             // vertex A
+    const float bpx = __fsub_rn(px, bx), bpy = __fsub_rn(py, by), bpz = __fsub_rn(pz, bz);
+    const float d3 = dot3_rn(abx, aby, abz, bpx, bpy, bpz);
+    const float d4 = dot3_rn(acx, acy, acz, bpx, bpy, bpz);
+    if (d3 >= 0.0f && d4 <= d3) { rx = bx; ry = by; rz = bz; return; }               // vertex B
+    const float vc = __fsub_rn(__fmul_rn(d1, d4), __fmul_rn(d3, d2));
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {                                    // edge AB
+        const float v = __fdiv_rn(d1, __fsub_rn(d1, d3));
+        rx = __fadd_rn(ax, __fmul_rn(abx, v)); ry = __fadd_rn(ay, __fmul_rn(aby, v));
+        rz = __fadd_rn(az, __fmul_rn(abz, v));
+        return;
+    }
+    const float cpx = __fsub_rn(px, cx), cpy = __fsub_rn(py, cy), cpz = __fsub_rn(pz, cz);
+    const float d5 = dot3_rn(abx, aby, abz, cpx, cpy, cpz);
+    const float d6 = dot3_rn(acx, acy, acz, cpx, cpy, cpz);
+    if (d6 >= 0.0f && d5 <= d6) { rx = cx; ry = cy; rz = cz; return; }               // vertex C
+    const float vb = __fsub_rn(__fmul_rn(d5, d2), __fmul_rn(d1, d6));
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {                                    // edge AC
+        const float w = __fdiv_rn(d2, __fsub_rn(d2, d6));
+        rx = __fadd_rn(ax, __fmul_rn(acx, w)); ry = __fadd_rn(ay, __fmul_rn(acy, w));
+        rz = __fadd_rn(az, __fmul_rn(acz, w));
+        return;
+    }
+    const float va = __fsub_rn(__fmul_rn(d3, d6), __fmul_rn(d5, d4));
+    const float d43 = __fsub_rn(d4, d3), d56 = __fsub_rn(d5, d6);
+    if (va <= 0.0f && d43 >= 0.0f && d56 >= 0.0f) {                                  // edge BC
+        const float w = __fdiv_rn(d43, __fadd_rn(d43, d56));
+        rx = __fadd_rn(__fmul_rn(__fsub_rn(cx, bx), w), bx);
+        ry = __fadd_rn(__fmul_rn(__fsub_rn(cy, by), w), by);
+        rz = __fadd_rn(__fmul_rn(__fsub_rn(cz, bz), w), bz);
+        return;
+    }
+    const float denom = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(va, vb), vc));           // face interior
+    const float v = __fmul_rn(vb, denom), w = __fmul_rn(vc, denom);
+    acx = __fmul_rn(acx, w); acy = __fmul_rn(acy, w); acz = __fmul_rn(acz, w);
+    rx = __fadd_rn(__fadd_rn(ax, __fmul_rn(abx, v)), acx);
+    ry = __fadd_rn(__fadd_rn(ay, __fmul_rn(aby, v)), acy);
+    rz = __fadd_rn(__fadd_rn(az, __fmul_rn(abz, v)), acz);
+}
+
+// S10: squared distance as Blender's len_squared_v3v3
+__device__ __forceinline__ float s10_d2(float px, float py, float pz, float rx, float ry, float rz)
+{
+    const float dx = __fsub_rn(rx, px), dy = __fsub_rn(ry, py), dz = __fsub_rn(rz, pz);
+    return dot3_rn(dx, dy, dz, dx, dy, dz);
+}
+
+// ---- index build ------------------------------------------------------------------------------
+// tri_xyz: n x 9 floats (a, b, c).  tris4: 3 float4 per triangle by ORIGINAL index (a.xyz|0, b, c).
+__global__ void k_tri_pack(const float* __restrict__ tri_xyz, long long n, float4* __restrict__ tris4,
+                           float4* __restrict__ centroids)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* t = tri_xyz + 9 * i;
+    tris4[3 * i] = make_float4(t[0], t[1], t[2], 0.0f);
+    tris4[3 * i + 1] = make_float4(t[3], t[4], t[5], 0.0f);
+    tris4[3 * i + 2] = make_float4(t[6], t[7], t[8], 0.0f);
+    centroids[i] = make_float4((t[0] + t[3] + t[6]) * (1.0f / 3.0f), (t[1] + t[4] + t[7]) * (1.0f / 3.0f),
+                               (t[2] + t[5] + t[8]) * (1.0f / 3.0f), 0.0f);
+}
+
+// sorted, run-padded triangles: 3 float4 each; .w of the first holds the local triangle index
+__global__ void k_tri_gather(const float4* __restrict__ tris4, const uint32_t* __restrict__ order, long long n,
+                             long long n_padded, float4* __restrict__ sorted)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    const float inf = __int_as_float(0x7f800000);
+    if (i < n) {
+        const uint32_t j = order[i];
+        float4 a = tris4[3 * (long long)j];
+        a.w = __uint_as_float(j);
+        sorted[3 * i] = a;
+        sorted[3 * i + 1] = tris4[3 * (long long)j + 1];
+        sorted[3 * i + 2] = tris4[3 * (long long)j + 2];
+    } else {
+        sorted[3 * i] = make_float4(inf, inf, inf, __uint_as_float(0xFFFFFFFFu));
+        sorted[3 * i + 1] = make_float4(inf, inf, inf, 0.0f);
+        sorted[3 * i + 2] = make_float4(inf, inf, inf, 0.0f);
+    }
+}
+
+__global__ void k_lbvh_fit_tris(const float4* __restrict__ sorted, long long n, int n_runs,
+                                BvhNode* __restrict__ nodes, const int* __restrict__ leaf_parent)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs || n_runs < 2) return;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int i = 0; i < TRI_LEAF; ++i) {
+        const long long j = (long long)r * TRI_LEAF + i;
+        if (j >= n) break;
+        for (int c = 0; c < 3; ++c) {
+            const float4 p = sorted[3 * j + c];
+            lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+            lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+            lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+        }
+    }
+    int child = ~r;
+    int node = leaf_parent[r];
+    while (node >= 0) {
+        BvhNode* nd = nodes + node;
+        const int off = (nd->left == child) ? 0 : 6;
+        volatile float* vb = nd->box;
+        for (int k = 0; k < 3; ++k) { vb[off + k] = lo[k]; vb[off + 3 + k] = hi[k]; }
+        __threadfence();
+        if (atomicAdd(&nd->arrived, 1u) == 0u) return;
+        __threadfence();
+        const int o2 = 6 - off;
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], vb[o2 + k]); hi[k] = fmaxf(hi[k], vb[o2 + 3 + k]); }
+        child = node;
+        node = nd->parent;
+    }
+}
+
+// ---- the walk: one thread per query -----------------------------------------------------------
+// keys[t] enters as "none" or as a warm-start candidate (previous winner re-evaluated by K1s).
+__global__ void __launch_bounds__(128)
+k_nn_surface(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
+             const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
+             long long n_queries, unsigned long long* __restrict__ keys, uint32_t index_offset,
+             float coord_extent, const int* __restrict__ stop_flag)
+{
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_queries) return;
+    const float x = qx[p], y = qy[p], z = qz[p];
+    const float inf = __int_as_float(0x7f800000);
+    // S9 returns a point that is within ~eta of the triangle, so its distance can undercut the
+    // box bound by eta; prune in DISTANCE terms:  sqrt(bound) > sqrt(best) + eta
+    const float eta = 3.9e-6f * fmaxf(fmaxf(fabsf(x), fabsf(y)), fmaxf(fabsf(z), coord_extent));   // 64 u * scale
+    unsigned long long best = keys[p];
+    float best_d = (best == KEY_NONE) ? inf : __uint_as_float((uint32_t)(best >> 32));
+    float prune_d = best_d + (2.0f * sqrtf(best_d) + eta) * eta;
+    int stack_ref[BVH_STACK];
+    float stack_bound[BVH_STACK];
+    int sp = 0;
+    int cur = (n_runs > 1) ? 0 : ~0;
+    const float4* nodes4 = reinterpret_cast<const float4*>(nodes);
+    while (true) {
+        if (cur < 0) {
+            const float4* lp = sorted + (long long)(~cur) * (TRI_LEAF * 3);
+#pragma unroll
+            for (int i = 0; i < TRI_LEAF; ++i) {
+                const float4 a = lp[3 * i], b = lp[3 * i + 1], c = lp[3 * i + 2];
+                if (a.x < inf) {
+                    float rx, ry, rz;
+                    closest_on_tri(x, y, z, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, rx, ry, rz);
+                    const float d = s10_d2(x, y, z, rx, ry, rz);
+                    if (d <= best_d && d < inf) {
+                        const unsigned long long k =
+                            ((unsigned long long)__float_as_uint(d) << 32) |
+                            (unsigned long long)(index_offset + __float_as_uint(a.w));
+                        if (k < best) {
+                            best = k; best_d = d;
+                            prune_d = best_d + (2.0f * sqrtf(best_d) + eta) * eta;
+                        }
+                    }
+                }
+            }
+        } else {
+            const float4 n0 = nodes4[4 * (long long)cur], n1 = nodes4[4 * (long long)cur + 1];
+            const float4 n2 = nodes4[4 * (long long)cur + 2], n3 = nodes4[4 * (long long)cur + 3];
+            const float bl = box_lower_bound(x, y, z, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+            const float br = box_lower_bound(x, y, z, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+            const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+            const bool left_first = bl <= br;
+            const int near = left_first ? left : right, far = left_first ? right : left;
+            const float bn = left_first ? bl : br, bf = left_first ? br : bl;
+            const bool take_near = !(bn * BVH_SHRINK > prune_d) && bn < inf;
+            const bool take_far = !(bf * BVH_SHRINK > prune_d) && bf < inf;
+            if (take_far && sp < BVH_STACK) { stack_ref[sp] = far; stack_bound[sp] = bf; ++sp; }
+            if (take_near) { cur = near; continue; }
+        }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (!(stack_bound[sp] * BVH_SHRINK > prune_d)) { cur = stack_ref[sp]; found = true; break; }
+        }
+        if (!found) break;
+    }
+    keys[p] = best;
+}
+
+}  // namespace icp

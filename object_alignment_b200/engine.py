@@ -138,6 +138,19 @@ class IcpEngine:
         self._check(self._lib.icp_set_base(self._h, xyz.ctypes.data, n, int(global_offset),
                                            int(n if n_global is None else n_global)))
 
+    def set_base_triangles(self, tri_xyz, global_offset=0, n_global=None):
+        """Surface mode (nn_mode=NN_SURFACE): upload this rank's shard of the base mesh's triangles
+        as (F, 9) corner coordinates -- the reference's real BVHTree.FromObject input."""
+        tri = np.ascontiguousarray(tri_xyz, dtype=np.float32).reshape(-1, 9)
+        n = tri.shape[0]
+        self._check(self._lib.icp_set_base_triangles(self._h, tri.ctypes.data, n, int(global_offset),
+                                                     int(n if n_global is None else n_global)))
+
+    def set_base_triangles_sharded(self, tri_xyz_full):
+        tri = np.asarray(tri_xyz_full).reshape(-1, 9)
+        lo, hi = shard_range(tri.shape[0], self.params.rank, self.params.world_size)
+        self.set_base_triangles(tri[lo:hi], lo, tri.shape[0])
+
     def set_base_sharded(self, xyz_full):
         """Upload only this rank's contiguous slice of the full base array."""
         xyz_full = np.asarray(xyz_full).reshape(-1, 3)

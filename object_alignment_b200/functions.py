@@ -28,7 +28,7 @@ import numpy as np
 from . import _native as N
 from .engine import IcpEngine, IcpError
 
-__all__ = ["VertexNN", "make_pairs", "affine_matrix_from_points", "calc_target", "icp_step",
+__all__ = ["VertexNN", "SurfaceNN", "base_index_from_object", "extract_triangles", "make_pairs", "affine_matrix_from_points", "calc_target", "icp_step",
            "extract_coords", "matrix_to_array", "array_to_matrix_like"]
 
 
@@ -44,6 +44,22 @@ def extract_coords(obj) -> np.ndarray:
         for i in range(n):
             co = verts[i].co
             buf[3 * i], buf[3 * i + 1], buf[3 * i + 2] = co[0], co[1], co[2]
+    return buf.reshape(n, 3)
+
+
+def extract_triangles(obj) -> np.ndarray:
+    """(F, 3) int32 vertex indices of the mesh's loop triangles (what BVHTree.FromObject walks);
+    empty for a face-less mesh (a point cloud)."""
+    mesh = obj.data
+    lt = getattr(mesh, "loop_triangles", None)
+    if lt is None:
+        return np.zeros((0, 3), dtype=np.int32)
+    if hasattr(mesh, "calc_loop_triangles"):
+        mesh.calc_loop_triangles()
+    n = len(lt)
+    buf = np.empty(n * 3, dtype=np.int32)
+    if n:
+        lt.foreach_get("vertices", buf)
     return buf.reshape(n, 3)
 
 
@@ -112,6 +128,42 @@ class VertexNN:
 
     def close(self):
         self.engine.close()
+
+
+class SurfaceNN(VertexNN):
+    """GPU closest-point-on-surface index over the base object's TRIANGLES: the reference's real
+    ``BVHTree.FromObject(base_obj, depsgraph)`` semantics (row N1).  ``find_nearest`` answers
+    come back as (triangle index, closest point) inside make_pairs / icp_step."""
+
+    def __init__(self, base_coords, triangles, **engine_kwargs):
+        engine_kwargs["nn_mode"] = N.NN_SURFACE
+        self.engine = IcpEngine(**engine_kwargs)
+        coords = np.ascontiguousarray(base_coords, dtype=np.float32).reshape(-1, 3)
+        tris = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+        self.n_base = tris.shape[0]
+        corners = np.ascontiguousarray(coords[tris].reshape(-1, 9))
+        if self.engine.params.world_size > 1:
+            self.engine.set_base_triangles_sharded(corners)
+        else:
+            self.engine.set_base_triangles(corners)
+        self._moving_key = None
+
+    @classmethod
+    def FromObject(cls, obj, depsgraph=None, **engine_kwargs):
+        return cls(extract_coords(obj), extract_triangles(obj), **engine_kwargs)
+
+
+# "auto": triangles when the base mesh has faces (the reference's behaviour), vertices for a
+# face-less point cloud (which the reference cannot align at all, SURVEY D2); or force one.
+DEFAULT_CORRESPONDENCE = "auto"
+
+
+def base_index_from_object(base_obj, depsgraph=None, correspondence=None, **engine_kwargs):
+    """The drop-in for ``BVHTree.FromObject(base_obj, depsgraph)`` (operators/icp_align.py:53)."""
+    mode = correspondence or DEFAULT_CORRESPONDENCE
+    if mode == "surface" or (mode == "auto" and len(extract_triangles(base_obj)) > 0):
+        return SurfaceNN.FromObject(base_obj, depsgraph, **engine_kwargs)
+    return VertexNN.FromObject(base_obj, depsgraph, **engine_kwargs)
 
 
 def _require_vertex_nn(base_bvh):

@@ -35,8 +35,9 @@ def rigid_matrix(angle_deg: float, translation, axis=_AXIS) -> np.ndarray:
     return m.astype(np.float32)
 
 
-def icosphere(frequency: int = 10) -> np.ndarray:
-    """Class-I geodesic icosahedron, unit radius: (10 f^2 + 2, 3) float32, deterministic order."""
+def icosphere(frequency: int = 10, return_faces: bool = False):
+    """Class-I geodesic icosahedron, unit radius: (10 f^2 + 2, 3) float32, deterministic order.
+    With return_faces also the (20 f^2, 3) int32 triangle list."""
     f = int(frequency)
     phi = (1 + math.sqrt(5)) / 2
     v = np.array([[-1, phi, 0], [1, phi, 0], [-1, -phi, 0], [1, -phi, 0],
@@ -49,20 +50,31 @@ def icosphere(frequency: int = 10) -> np.ndarray:
              (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
     seen = {}
     out = []
+    tris = []
     for (a, b, c) in faces:
+        local = {}
         for i in range(f + 1):
             for j in range(f + 1 - i):
                 k = f - i - j
                 # integer barycentric key on the (sorted) corner ids makes shared points unique
                 key = tuple(sorted(((a, i), (b, j), (c, k))))
                 key = tuple((cid, w) for cid, w in key if w != 0)
-                if key in seen:
-                    continue
-                seen[key] = len(out)
-                p = (i * v[a] + j * v[b] + k * v[c]) / f
-                out.append(p / np.linalg.norm(p))
+                if key not in seen:
+                    seen[key] = len(out)
+                    p = (i * v[a] + j * v[b] + k * v[c]) / f
+                    out.append(p / np.linalg.norm(p))
+                local[(i, j)] = seen[key]
+        for i in range(f):
+            for j in range(f - i):
+                tris.append((local[(i, j)], local[(i + 1, j)], local[(i, j + 1)]))
+                if i + j < f - 1:
+                    tris.append((local[(i + 1, j)], local[(i + 1, j + 1)], local[(i, j + 1)]))
     pts = np.array(out, dtype=np.float64)
     assert pts.shape[0] == 10 * f * f + 2, pts.shape
+    if return_faces:
+        t = np.array(tris, dtype=np.int32)
+        assert t.shape[0] == 20 * f * f, t.shape
+        return pts.astype(np.float32), t
     return pts.astype(np.float32)
 
 
@@ -80,6 +92,25 @@ def bunny_like(n: int, seed: int, noise: float = 0.0) -> np.ndarray:
     if noise > 0:
         p = p + rng.normal(0.0, noise, size=p.shape)
     return p.astype(np.float32)
+
+
+def bunny_like_mesh(n: int, seed: int):
+    """The lobed test surface as a watertight triangle mesh: n vertices (float32) and the
+    (2n - 4, 3) int32 triangles of the convex hull of their unit directions (a Delaunay
+    triangulation of the sphere, carried to the star-shaped surface)."""
+    from scipy.spatial import ConvexHull
+
+    rng = np.random.default_rng(seed)
+    u = rng.standard_normal((n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    verts = bunny_like(n, seed)
+    tris = ConvexHull(u).simplices.astype(np.int32)
+    return verts, tris
+
+
+def triangle_corners(verts: np.ndarray, tris: np.ndarray) -> np.ndarray:
+    """(F, 9) float32 corner coordinates a.xyz, b.xyz, c.xyz (the icp_set_base_triangles layout)."""
+    return np.ascontiguousarray(np.asarray(verts, np.float32)[np.asarray(tris)].reshape(-1, 9))
 
 
 def apply_rigid(points: np.ndarray, angle_deg: float, translation, axis=_AXIS) -> np.ndarray:

@@ -19,7 +19,8 @@ import numpy as np
 
 from . import _native as N
 from .engine import IcpError, stride_from_sample_fraction
-from .functions import VertexNN, array_to_matrix_like, extract_coords, matrix_to_array
+from .functions import (array_to_matrix_like, base_index_from_object, extract_coords,
+                        matrix_to_array)
 from .preferences import get_addon_preferences
 
 try:  # inside Blender
@@ -106,6 +107,7 @@ class OBJECT_OT_icp_align(Operator):
     # engine knobs that have no counterpart in the reference's preferences
     device = 0
     reject_fraction = 0.0
+    correspondence = None      # None -> functions.DEFAULT_CORRESPONDENCE ("auto": surface if the base has faces)
 
     @classmethod
     def poll(cls, context):
@@ -127,8 +129,8 @@ class OBJECT_OT_icp_align(Operator):
             # the reference's make_pairs returns None here and the unpack at icp_align.py:101 raises
             raise TypeError("cannot unpack non-iterable NoneType object")
 
-        base_nn = VertexNN.FromObject(
-            base_obj, context.evaluated_depsgraph_get(), device=self.device, thresh=thresh,
+        base_nn = base_index_from_object(
+            base_obj, context.evaluated_depsgraph_get(), self.correspondence, device=self.device, thresh=thresh,
             target_d=settings.target_d, use_target=settings.use_target,
             align_meth=settings.align_meth, stride=factor, reject_fraction=self.reject_fraction)
         try:
@@ -178,6 +180,7 @@ class OBJECT_OT_icp_align_feedback(Operator):
 
     device = 0
     reject_fraction = 0.0
+    correspondence = None
     _timer = None
 
     @classmethod
@@ -203,8 +206,8 @@ class OBJECT_OT_icp_align_feedback(Operator):
         thresh = settings.min_start
         if not thresh > 0:
             raise TypeError("cannot unpack non-iterable NoneType object")
-        self.base_nn = VertexNN.FromObject(
-            self.base_obj, context.evaluated_depsgraph_get(), device=self.device, thresh=thresh,
+        self.base_nn = base_index_from_object(
+            self.base_obj, context.evaluated_depsgraph_get(), self.correspondence, device=self.device, thresh=thresh,
             target_d=settings.target_d, use_target=settings.use_target, align_meth=settings.align_meth,
             stride=stride_from_sample_fraction(settings.sample_fraction),
             reject_fraction=self.reject_fraction)

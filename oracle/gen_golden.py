@@ -76,6 +76,20 @@ def scenarios():
     S.append(dict(name="c1_tight_thresh", moving=c1["moving"], base=c1["base"],
                   prefs=dict(sample_fraction=1.0, icp_iterations=10, use_target=True,
                              min_start=0.06, target_d=0.0)))
+    # ---- surface scenarios (row N1): the base HAS faces, the provider answers with the closest
+    #      point on the triangulated surface -- the reference's real semantics
+    sv, st = meshgen.icosphere(10, return_faces=True)
+    S.append(dict(name="surf_c1_fixed12", moving=c1["moving"], base=sv, base_faces=st,
+                  prefs=dict(sample_fraction=1.0, icp_iterations=12, use_target=False)))
+    S.append(dict(name="surf_c1_defaults", moving=c1["moving"], base=sv, base_faces=st, prefs=dict()))
+    S.append(dict(name="surf_c1_worldmats", moving=mv_local, base=sv, base_faces=st,
+                  mw_align=align_w, mw_base=base_w,
+                  prefs=dict(sample_fraction=1.0, icp_iterations=8, use_target=True,
+                             min_start=0.35, target_d=0.002)))
+    bv, bt = meshgen.bunny_like_mesh(1500, 110)
+    bm = meshgen.apply_rigid(meshgen.bunny_like(1200, 111, noise=2e-3), 4.0, (0.02, -0.01, 0.03))
+    S.append(dict(name="surf_bunny_1k", moving=bm, base=bv, base_faces=bt,
+                  prefs=dict(sample_fraction=1.0, icp_iterations=10, use_target=False, min_start=0.5)))
     S.append(dict(name="cloud_2k_3k", moving=cloud["moving"], base=cloud["base"],
                   prefs=dict(sample_fraction=1.0, icp_iterations=15, use_target=False,
                              min_start=0.5)))
@@ -85,8 +99,13 @@ def scenarios():
 def run_reference(sc):
     general, icp_align = ref_loader.load_reference()
     align = ms.Object("align", sc["moving"], sc.get("mw_align"), sc.get("groups"))
-    base = ms.Object("base", sc["base"], sc.get("mw_base"))
+    base = ms.Object("base", sc["base"], sc.get("mw_base"), faces=sc.get("base_faces"))
     prefs = ms.Settings(**sc["prefs"])
+    from mathutils import bvhtree as _bvhtree_stub      # the stub module the reference imported from
+    _bvhtree_stub.BVHTree = (icp_oracle.NearestSurfaceBVH if sc.get("base_faces") is not None
+                             else icp_oracle.NearestVertexBVH)
+    icp_align_mod = ref_loader.load_reference()[1]
+    icp_align_mod.BVHTree = _bvhtree_stub.BVHTree
     rec = dict(idx=[], K=[], d_stats=[], M=[], vl=None)
     bvh_box = {}
 
@@ -152,6 +171,8 @@ def main():
         for gname, (mask, w) in (sc.get("groups") or {}).items():
             out["group_%s_mask" % gname] = np.asarray(mask, bool)
             out["group_%s_weight" % gname] = np.asarray(w, np.float32)
+        if sc.get("base_faces") is not None:
+            out["base_faces"] = np.asarray(sc["base_faces"], np.int32)
         out["group_order"] = np.array(list((sc.get("groups") or {}).keys()), dtype="U32")
         path = os.path.join(OUT, sc["name"] + ".npz")
         np.savez_compressed(path, **out)

@@ -60,6 +60,11 @@ def _lib():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
         ]
         lib.oracle_num_threads.restype = ctypes.c_int
+        lib.oracle_nn_surface_bruteforce.restype = ctypes.c_int
+        lib.oracle_nn_surface_bruteforce.argtypes = [
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+        ]
         _LIB = lib
     return _LIB
 
@@ -86,6 +91,50 @@ def nn_bruteforce(q: np.ndarray, base: np.ndarray, index_offset: int = 0, thread
     if rc != 0:
         raise MemoryError("oracle_nn_bruteforce")
     return idx, d2
+
+
+def nn_surface_bruteforce(q: np.ndarray, tri_xyz: np.ndarray, index_offset: int = 0, threads: int = 0):
+    """Closest point on the triangulated surface for each query (rules S9 / S10; restates the
+    reference's real query, icp_align.py:53 + general.py:297):
+    (triangle idx int32[M], d2 float32[M], closest point float32[M,3]); ties -> lowest triangle."""
+    q = np.ascontiguousarray(q, dtype=f32).reshape(-1, 3)
+    tri = np.ascontiguousarray(tri_xyz, dtype=f32).reshape(-1, 9)
+    m = q.shape[0]
+    idx = np.empty(m, dtype=np.int32)
+    d2 = np.empty(m, dtype=f32)
+    co = np.empty((m, 3), dtype=f32)
+    _lib().oracle_nn_surface_bruteforce(q.ctypes.data, m, tri.ctypes.data, tri.shape[0], int(index_offset),
+                                        idx.ctypes.data, d2.ctypes.data, co.ctypes.data, int(threads))
+    return idx, d2, co
+
+
+class NearestSurfaceBVH:
+    """Drop-in for ``BVHTree.FromObject(base_obj, depsgraph)`` with the reference's REAL semantics:
+    ``find_nearest(co)`` -> (closest point on the triangulated surface, None, triangle index, dist).
+    Brute force over the triangles (exact under S9/S10); for golden generation at small sizes."""
+
+    def __init__(self, coords, tris):
+        coords = np.ascontiguousarray(coords, dtype=f32).reshape(-1, 3)
+        self.tri_xyz = np.ascontiguousarray(coords[np.asarray(tris)].reshape(-1, 9))
+        self.log = []
+
+    @classmethod
+    def FromObject(cls, obj, depsgraph=None):
+        n = len(obj.data.vertices)
+        buf = np.empty(n * 3, dtype=f32)
+        obj.data.vertices.foreach_get("co", buf)
+        lt = obj.data.loop_triangles
+        tb = np.empty(len(lt) * 3, dtype=np.int32)
+        lt.foreach_get("vertices", tb)
+        return cls(buf.reshape(-1, 3), tb.reshape(-1, 3))
+
+    def find_nearest(self, co):
+        if self.tri_xyz.shape[0] == 0:
+            return (None, None, None, None)
+        q = np.array([co[0], co[1], co[2]], dtype=f32).reshape(1, 3)
+        idx, d2, pt = nn_surface_bruteforce(q, self.tri_xyz, threads=1)
+        self.log.append(int(idx[0]))
+        return (ms.Vector(pt[0]), None, int(idx[0]), math.sqrt(float(d2[0])))
 
 
 def pack_key(d2: np.ndarray, idx: np.ndarray) -> np.ndarray:
@@ -277,7 +326,7 @@ def percentile_keep_port(dist: np.ndarray, reject_fraction: float) -> np.ndarray
 
 
 def make_pairs_vec(coords, vlist, mw_align, mw_base, base, thresh, sample=0, calc_stats=False,
-                   reject_fraction=0.0, nn="brute", index_offset=0, return_all=False):
+                   reject_fraction=0.0, nn="brute", index_offset=0, return_all=False, tri_xyz=None):
     """numpy-vectorised restatement of make_pairs (general.py:257-329), nearest-vertex variant.
 
     coords: (M,3) fp32 align-local vertices; vlist: int indices (already masked);
@@ -298,12 +347,15 @@ def make_pairs_vec(coords, vlist, mw_align, mw_base, base, thresh, sample=0, cal
         vl = vl[0::sample]
     a = coords[vl]
     q = matvec43_vec(imx2, matvec43_vec(mx1, a))                      # general.py:287
-    if nn == "brute":
+    if tri_xyz is not None:                                           # surface variant (N1)
+        idx, d2, co1 = nn_surface_bruteforce(q, tri_xyz, index_offset=index_offset)
+    elif nn == "brute":
         idx, d2 = nn_bruteforce(q, base, index_offset=index_offset)   # general.py:297 (D2)
+        co1 = base[idx - index_offset]
     else:
         idx, d2 = nn_kdtree_exact(q, base)
         idx = idx + np.int32(index_offset)
-    co1 = base[idx - index_offset]
+        co1 = base[idx - index_offset]
     wq = matvec43_vec(mx2, q)
     w1 = matvec43_vec(mx2, co1)
     dist = length3_vec((wq - w1).astype(f32))                         # general.py:299
@@ -402,7 +454,7 @@ def rotation_angle(m44: np.ndarray) -> float:
 
 def icp_execute_port(coords, vlist, mw_align, mw_base, base, *, thresh=0.5, sample_fraction=0.5,
                      iters=50, target_d=0.01, use_target=True, align_meth="0",
-                     reject_fraction=0.0, nn="brute", record=False):
+                     reject_fraction=0.0, nn="brute", record=False, tri_xyz=None):
     """The iteration loop of OBJECT_OT_icp_align.execute (icp_align.py:82-151), vectorised.
 
     Per iteration: make_pairs (:101) -> solver (:106-109) -> fp32 copy of M (:116-119) ->
@@ -420,7 +472,7 @@ def icp_execute_port(coords, vlist, mw_align, mw_base, base, *, thresh=0.5, samp
     while n < iters and not converged:
         res = make_pairs_vec(coords, vlist, mw, mw_base, base, thresh, factor,
                              calc_stats=use_target, reject_fraction=reject_fraction, nn=nn,
-                             return_all=True)
+                             return_all=True, tri_xyz=tri_xyz)
         if res is None:
             raise TypeError("cannot unpack non-iterable NoneType object")  # icp_align.py:101
         M = affine_matrix_from_points_port(res["A"], res["B"], scale=(align_meth == "1"))

@@ -306,9 +306,27 @@ class _VertexSeq:
         np.asarray(buf).reshape(-1)[:] = self._co.reshape(-1)
 
 
+class _LoopTriangles:
+    """``mesh.loop_triangles`` with Blender's bulk ``foreach_get("vertices", buf)``."""
+
+    def __init__(self, tris):
+        self._t = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+
+    def __len__(self):
+        return self._t.shape[0]
+
+    def foreach_get(self, attr, buf):
+        assert attr == "vertices"
+        np.asarray(buf).reshape(-1)[:] = self._t.reshape(-1)
+
+
 class Mesh:
-    def __init__(self, coords_f32, group_members=None):
+    def __init__(self, coords_f32, group_members=None, faces=None):
         self.vertices = _VertexSeq(coords_f32, group_members)
+        self.loop_triangles = _LoopTriangles(faces if faces is not None else np.zeros((0, 3), np.int32))
+
+    def calc_loop_triangles(self):
+        pass
 
 
 class VertexGroup:
@@ -343,7 +361,7 @@ class Object:
     ``groups`` maps group name -> (member_mask bool[M], weight float32[M]).
     """
 
-    def __init__(self, name, coords, matrix_world=None, groups=None):
+    def __init__(self, name, coords, matrix_world=None, groups=None, faces=None):
         self.name = name
         self.type = "MESH"
         self.rotation_mode = "XYZ"
@@ -354,7 +372,7 @@ class Object:
             vgs.append(VertexGroup(gname, gi))
             members[gi] = (np.asarray(mask, dtype=bool), np.asarray(w, dtype=f32))
         self.vertex_groups = _VertexGroups(vgs)
-        self.data = Mesh(coords, members)
+        self.data = Mesh(coords, members, faces)
         self.tag_count = 0
 
     def update_tag(self):

@@ -127,3 +127,91 @@ int oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* ================================================================================================
+ * Surface variant: closest point on the TRIANGULATED SURFACE, i.e.
+ * what the reference really asks of Blender: BVHTree.FromObject(base_obj, depsgraph)
+ * (/root/reference/operators/icp_align.py:53) and base_bvh.find_nearest(co_find)
+ * (/root/reference/functions/general.py:297).  Blender's C BVH (mathutils.bvhtree, Blender 3.2.2) is
+ * not in /root/reference; restated here is its published per-triangle arithmetic:
+ *   S9   closest_on_tri_to_point_v3 -- Ericson's region walk, every operation a separate fp32
+ *        rounding (this file is compiled with -ffp-contract=off)
+ *   S10  len_squared_v3v3           -- (dx*dx + dy*dy) + dz*dz
+ * The winner is the smallest S10 distance; ties go to the LOWEST triangle index (Blender's own
+ * tie-break depends on its tree layout).
+ * ================================================================================================ */
+static inline float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+void oracle_closest_on_tri(const float *p, const float *a, const float *b, const float *c, float *r)
+{
+    float ab[3], ac[3], ap[3], bp[3], cp[3];
+    for (int i = 0; i < 3; ++i) { ab[i] = b[i] - a[i]; ac[i] = c[i] - a[i]; ap[i] = p[i] - a[i]; }
+    const float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; return; }
+    for (int i = 0; i < 3; ++i) bp[i] = p[i] - b[i];
+    const float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) { r[0] = b[0]; r[1] = b[1]; r[2] = b[2]; return; }
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+        const float v = d1 / (d1 - d3);
+        for (int i = 0; i < 3; ++i) r[i] = a[i] + ab[i] * v;
+        return;
+    }
+    for (int i = 0; i < 3; ++i) cp[i] = p[i] - c[i];
+    const float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) { r[0] = c[0]; r[1] = c[1]; r[2] = c[2]; return; }
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        const float w = d2 / (d2 - d6);
+        for (int i = 0; i < 3; ++i) r[i] = a[i] + ac[i] * w;
+        return;
+    }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        for (int i = 0; i < 3; ++i) { float t = c[i] - b[i]; t = t * w; r[i] = t + b[i]; }
+        return;
+    }
+    const float denom = 1.0f / (va + vb + vc);
+    const float v = vb * denom, w = vc * denom;
+    for (int i = 0; i < 3; ++i) {
+        const float acw = ac[i] * w;
+        float t = a[i] + ab[i] * v;
+        r[i] = t + acw;
+    }
+}
+
+float oracle_len_squared(const float *p, const float *r)
+{
+    const float d[3] = {r[0] - p[0], r[1] - p[1], r[2] - p[2]};
+    return dot3(d, d);
+}
+
+/* Brute force over all triangles (tri_xyz: F x 9 floats).  co_out (nullable): M x 3 closest points. */
+int oracle_nn_surface_bruteforce(const float *q_xyz, int64_t M, const float *tri_xyz, int64_t F,
+                                 int32_t index_offset, int32_t *idx_out, float *d2_out, float *co_out,
+                                 int threads)
+{
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < M; ++i) {
+        const float *p = q_xyz + 3 * i;
+        float best = INFINITY, br[3] = {0, 0, 0};
+        int64_t bi = -1;
+        for (int64_t f = 0; f < F; ++f) {
+            const float *t = tri_xyz + 9 * f;
+            float r[3];
+            oracle_closest_on_tri(p, t, t + 3, t + 6, r);
+            const float d = oracle_len_squared(p, r);
+            if (d < best) { best = d; bi = f; br[0] = r[0]; br[1] = r[1]; br[2] = r[2]; }
+        }
+        idx_out[i] = bi < 0 ? -1 : (int32_t)(bi + index_offset);
+        d2_out[i] = best;
+        if (co_out) { co_out[3 * i] = br[0]; co_out[3 * i + 1] = br[1]; co_out[3 * i + 2] = br[2]; }
+    }
+    return 0;
+}

@@ -31,3 +31,4 @@ class Golden:
         self.K, self.d_stats, self.M = z["K"], z["d_stats"], z["M"]
         self.matrix_world = z["matrix_world"]
         self.vlist = z["vlist"]
+        self.base_faces = z["base_faces"] if "base_faces" in z.files else None

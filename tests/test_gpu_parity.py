@@ -286,7 +286,7 @@ def test_bvh_trajectory_matches_bruteforce(name):
 # ------------------------------------------------------------------ make_pairs / solver API
 def _objects(g):
     align = ms.Object("align", g.moving, g.mw_align, g.groups)
-    base = ms.Object("base", g.base, g.mw_base)
+    base = ms.Object("base", g.base, g.mw_base, faces=g.base_faces)      # faces -> surface mode (N1)
     return align, base
 
 
@@ -439,7 +439,7 @@ def test_reference_shaped_loop_with_icp_step():
         nn.close()
 
 
-@pytest.mark.parametrize("name", ["c1_fixed20", "c1_defaults", "c1_include"])
+@pytest.mark.parametrize("name", ["c1_fixed20", "c1_defaults", "c1_include", "surf_c1_defaults"])
 def test_modal_operator_matches_reference_golden(name):
     """Row N3: the timer-driven operator reaches the same pose in the same number of iterations."""
     g = Golden(name)
@@ -469,6 +469,89 @@ def test_modal_operator_matches_reference_golden(name):
     op2.invoke(ctx2, ms.Event("NONE"))
     op2.modal(ctx2, ms.Event("TIMER"))
     assert op2.modal(ctx2, ms.Event("ESC")) == {"CANCELLED"} and op2.base_nn is None
+
+
+# ------------------------------------------------------------------ N1: closest point on the surface
+def _surface_case(case):
+    rng = np.random.default_rng(91)
+    if case == "icosphere":
+        v, t = meshgen.icosphere(12, return_faces=True)
+        q = (v[rng.integers(0, len(v), 4000)] * (1 + 0.05 * rng.standard_normal((4000, 1)))).astype(np.float32)
+    elif case == "bunny":
+        v, t = meshgen.bunny_like_mesh(20_000, 92)
+        q = meshgen.apply_rigid(meshgen.bunny_like(15_000, 93, noise=2e-3), 3.0, (0.02, -0.01, 0.03))
+    elif case == "far":
+        v, t = meshgen.bunny_like_mesh(6000, 94)
+        q = ((rng.random((3000, 3)) - 0.5) * 12).astype(np.float32)
+    elif case == "on_vertices":        # queries exactly on mesh vertices: d2 == 0, many tied triangles
+        v, t = meshgen.icosphere(8, return_faces=True)
+        q = v.copy()
+    elif case == "single_triangle":
+        v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+        t = np.array([[0, 1, 2]], np.int32)
+        q = ((rng.random((500, 3)) - 0.3) * 2).astype(np.float32)
+    return v, t, q
+
+
+@pytest.mark.parametrize("case", ["icosphere", "bunny", "far", "on_vertices", "single_triangle"])
+def test_surface_search_matches_oracle(case):
+    v, t, q = _surface_case(case)
+    tri = meshgen.triangle_corners(v, t)
+    with IcpEngine(nn_mode=2, thresh=1e9) as e:
+        e.set_base_triangles(tri)
+        e.set_moving(q)
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+        idx2, d22 = e.nn()                       # warm-started second pass
+        A, B, ds = e.make_pairs(calc_stats=True)
+    oi, od, oc = orc.nn_surface_bruteforce(q, tri)
+    assert np.array_equal(idx, oi) and np.array_equal(idx2, oi)
+    assert np.array_equal(d2.view(np.uint32), od.view(np.uint32)) and np.array_equal(d22, od)
+    assert np.array_equal(B, oc.astype(np.float64).T)            # targets = closest points (identity poses)
+    assert np.array_equal(A, q.astype(np.float64).T)
+
+
+@pytest.mark.parametrize("name", ["surf_c1_fixed12", "surf_c1_worldmats", "surf_bunny_1k"])
+def test_surface_stepwise_parity(name):
+    g = Golden(name)
+    p = g.prefs
+    tri = g.base[g.base_faces].reshape(-1, 9)
+    vlist = orc.build_vlist_port(g.moving.shape[0], g.groups)
+    stride = orc.stride_factor_port(p["sample_fraction"])
+    with IcpEngine(thresh=p["min_start"], target_d=p["target_d"], use_target=p["use_target"],
+                   align_meth=p["align_meth"], stride=stride, nn_mode=2) as e:
+        e.set_base_triangles(tri)
+        e.set_moving(g.moving, vlist)
+        e.set_matrices(g.mw_align, g.mw_base)
+        for it in range(min(6, g.iterations)):
+            mw = e.matrix_world()
+            res = orc.make_pairs_vec(g.moving, vlist, mw, g.mw_base, g.base, p["min_start"], stride,
+                                     calc_stats=True, return_all=True, tri_xyz=tri)
+            idx, d2 = e.nn()
+            assert np.array_equal(idx, res["idx"]) and np.array_equal(d2, res["d2"])
+            A, B, ds = e.make_pairs(calc_stats=True)
+            assert np.array_equal(A, res["A"]) and np.array_equal(B, res["B"])
+            M, st = e.step()
+            assert st.pairs == int(res["keep"].sum())
+            np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(res["A"], res["B"]), atol=1e-10)
+
+
+def test_surface_mode_needs_triangles():
+    with IcpEngine(nn_mode=2) as e:
+        e.set_base(_rand_cloud(100, 1))
+        e.set_moving(_rand_cloud(10, 2))
+        e.set_matrices(np.eye(4), np.eye(4))
+        with pytest.raises(IcpError) as ei:
+            e.nn()
+        assert ei.value.code == 6
+    base_cloud = ms.Object("b", _rand_cloud(50, 3))                   # no faces -> vertex index
+    nn = oab.base_index_from_object(base_cloud)
+    assert type(nn) is oab.VertexNN
+    nn.close()
+    v, t = meshgen.icosphere(2, return_faces=True)
+    nn = oab.base_index_from_object(ms.Object("m", v, faces=t))
+    assert type(nn) is oab.SurfaceNN
+    nn.close()
 
 
 # ------------------------------------------------------------------ percentile rejection (new)
