@@ -38,6 +38,8 @@ WORKLOADS = {
     "c3": (1_000_000, 1_000_000, 200, 201, "C3: 1M moving vs 1M base bunny-like clouds"),
     "c4": (1_000_000, 10_000_000, 300, 301, "C4: 1M moving vs 10M base, base sharded across ranks"),
     "c5": (5_000_000, 5_000_000, 500, 501, "C5: 5M vs 5M, 25% outliers, reject_fraction 0.25, icp_include mask"),
+    "c2s": (100_000, 100_000, 100, 101, "C2 surface: 100k moving vs a 100k-vertex / 200k-triangle base MESH (closest point on surface)"),
+    "c3s": (1_000_000, 1_000_000, 200, 201, "C3 surface: 1M moving vs a 1M-vertex / 2M-triangle base MESH (closest point on surface)"),
 }
 
 
@@ -53,7 +55,12 @@ def make_workload(name):
         cfg["vlist"] = build_vlist_from_arrays(cfg["moving"].shape[0], cfg["groups"])   # icp_align.py:56-80
         return cfg
     m, n, sb, sm, _ = WORKLOADS[name]
-    return meshgen.config_cloud(m, n, sb, sm)
+    cfg = meshgen.config_cloud(m, n, sb, sm)
+    if name.endswith("s"):
+        verts, tris = meshgen.bunny_like_mesh(n, sb)
+        cfg["base"] = verts
+        cfg["triangles"] = meshgen.triangle_corners(verts, tris)
+    return cfg
 
 
 class ClockSampler:
@@ -227,15 +234,31 @@ def run_ours(args, rank, world, local_rank):
     ident = np.eye(4, dtype=np.float32)
 
     nn_mode = 1 if args.nn_mode == "bvh" else 0
+    surface = "triangles" in cfg
+    if surface:
+        nn_mode = 2
+    shard_q = args.shard == "queries" or (args.shard == "auto" and nn_mode != 0)
     vlist = cfg.get("vlist")
     m_eff = int(vlist.shape[0]) if vlist is not None else m
     eng = IcpEngine(thresh=cfg["thresh"], use_target=False, align_meth="0", stride=1,
                     device=local_rank, rank=rank, world_size=world, nn_variant=args.nn_variant,
-                    nn_mode=nn_mode, reject_fraction=cfg.get("reject_fraction", 0.0))
+                    nn_mode=nn_mode, reject_fraction=cfg.get("reject_fraction", 0.0),
+                    shard_mode=1 if (shard_q and world > 1) else 0)
     t0 = time.perf_counter()
-    eng.set_base_sharded(base)
+    if surface:
+        eng.set_base_triangles(cfg["triangles"]) if shard_q or world == 1 else eng.set_base_triangles_sharded(cfg["triangles"])
+    elif shard_q and world > 1:
+        eng.set_base(base)
+    else:
+        eng.set_base_sharded(base)
     base_upload_s = time.perf_counter() - t0
     icpdist.connect_engine(eng, dist)
+    if shard_q and world > 1:
+        # this rank's contiguous slice of the (already sampled) query positions
+        from object_alignment_b200 import shard_range
+        pos = np.arange(m, dtype=np.int32) if vlist is None else vlist
+        lo, hi = shard_range(pos.shape[0], rank, world)
+        vlist = np.ascontiguousarray(pos[lo:hi])
     pinned = PinnedArray(mov.shape, np.float32)
     pinned.array[...] = mov
     eng.set_moving(pinned.array, vlist)
@@ -311,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    n_local = n // world
+    n_local = n if (shard_q and world > 1) else n // world
     nn_avg_ms = nn_ms / max(nn_launches, 1)
     m_all, m = m, m_eff                                        # work is counted on the sampled queries
     flops = 8.0 * m * n_local                                  # 8 FLOP per (query, base) pair
@@ -321,9 +344,11 @@ def run_ours(args, rank, world, local_rank):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "nn_traffic.json"))).get(args.workload)
     except (OSError, ValueError):
         pass
-    if nn_mode == 1:
-        line_roofline = bvh_roofline(m, n_local, nn_avg_ms, hbm_peak_of(peaks), args.workload)
-    roofline = line_roofline if nn_mode == 1 else {
+    if nn_mode != 0:
+        line_roofline = bvh_roofline(m // (world if shard_q else 1), n_local, nn_avg_ms, hbm_peak_of(peaks), args.workload)
+        if surface:
+            line_roofline["kernel"] = "k_nn_surface"
+    roofline = line_roofline if nn_mode != 0 else {
         "kernel": "k_nn_bruteforce_filter<4,3>" if (args.nn_variant in (0, 20) and n_local >= 262144) else "k_nn_bruteforce",
         "bound": "fp32",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
@@ -355,11 +380,12 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][4], "n_moving": m_all, "m_eff": m, "n_base": n,
-                   "reject_fraction": cfg.get("reject_fraction", 0.0), "base_shards": world,
+                   "reject_fraction": cfg.get("reject_fraction", 0.0), "base_shards": 1 if (shard_q and world > 1) else world, "query_shards": world if (shard_q and world > 1) else 1,
                    "thresh": cfg["thresh"] if np.isfinite(cfg["thresh"]) else "inf", "sample_fraction": 1.0,
-                   "align_meth": "RIGID", "nn_mode": args.nn_mode, "nn_variant": args.nn_variant,
+                   "align_meth": "RIGID", "nn_mode": "surface" if surface else args.nn_mode, "nn_variant": args.nn_variant,
                    "l2": "flushed between timed steps (256 MB memset)",
-                   "collectives": "ncclAllReduce MIN u64[M] + SUM f64[20] per step" if world > 1 else "none"},
+                   "collectives": ("none" if world == 1 else "ncclAllReduce SUM f64[20] per step" if shard_q
+                                   else "ncclAllReduce MIN u64[M] + SUM f64[20] per step")},
         "correspondences_per_sec": value * m,
         "pair_evals_per_sec": value * m * n,
         "e2e": {"value": args.steps / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d,
@@ -375,12 +401,12 @@ def run_ours(args, rank, world, local_rank):
         "final_pose_row0": [float(x) for x in final_pose[0]],
     }
     eng.close()
-    if world == 1 and not args.no_secondary and vlist is None and not cfg.get("reject_fraction"):
+    if world == 1 and not args.no_secondary and vlist is None and not cfg.get("reject_fraction") and not surface:
         other = 0 if nn_mode == 1 else 1
         line["next_rows" if other == 1 else "north_star_kernel"] = {
             ("N2_bvh_search" if other == 1 else "bruteforce"): measure_secondary(
                 cfg, local_rank, other, args.steps if other == 1 else min(args.steps, 5), 3)}
-    if world == 1 and not args.no_cpu and vlist is None:
+    if world == 1 and not args.no_cpu and vlist is None and not surface:
         line["cpu_baseline"] = cpu_baseline(cfg, args.cpu_sample, 2)
         line["cpu_fair"] = cpu_fair_comparator(cfg)
     print(json.dumps(line), flush=True)
@@ -457,6 +483,9 @@ def main():
                     help="bruteforce = the north-star O(M N) kernel (default, primary line); "
                          "bvh = row N2, the exact spatially-indexed search")
     ap.add_argument("--cpu-sample", type=int, default=20_000)
+    ap.add_argument("--shard", default="auto", choices=["auto", "base", "queries"],
+                    help="multi-GPU split: base (north star: keys all-reduce MIN) or queries (replicated base, "
+                         "only the 20-double moment sum); auto = base for bruteforce, queries for bvh/surface")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()

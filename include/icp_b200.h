@@ -48,6 +48,14 @@ typedef enum icp_nn_mode {
                               icp_set_base_triangles instead of icp_set_base */
 } icp_nn_mode;
 
+typedef enum icp_shard_mode {
+    ICP_SHARD_BASE = 0,    /* base vertices split across ranks, queries replicated; per iteration
+                              ncclAllReduce MIN over the uint64 keys + SUM over 20 doubles (north star) */
+    ICP_SHARD_QUERIES = 1  /* base replicated, every rank owns a slice of the queries (pass only that
+                              slice to icp_set_moving); the only exchange is the 20-double SUM.  The
+                              right split for the O(log N) searches (BVH / surface)              */
+} icp_shard_mode;
+
 /* Parameter block; mirrors ObjectAlignmentPreferences (lib/preferences.py:31-72) as read by
  * execute (operators/icp_align.py:48-49,82-89).  Set struct_size = sizeof(icp_params). */
 typedef struct icp_params {
@@ -64,7 +72,7 @@ typedef struct icp_params {
     int32_t rank;            /* this process's rank among the base shards (0 when single GPU)   */
     int32_t world_size;      /* number of base shards / GPUs (1 when single GPU)                 */
     int32_t nn_variant;      /* kernel variant for tuning: 0 = library default                   */
-    int32_t reserved;
+    int32_t shard_mode;      /* icp_shard_mode when world_size > 1                               */
 } icp_params;
 
 /* One record per executed iteration (what execute prints/uses at icp_align.py:129-149). */

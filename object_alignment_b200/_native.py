@@ -24,6 +24,9 @@ NN_BRUTEFORCE = 0
 NN_BVH = 1
 NN_SURFACE = 2
 
+SHARD_BASE = 0
+SHARD_QUERIES = 1
+
 
 class IcpParams(C.Structure):
     """Mirror of `icp_params` (include/icp_b200.h)."""
@@ -41,7 +44,7 @@ class IcpParams(C.Structure):
         ("rank", C.c_int32),
         ("world_size", C.c_int32),
         ("nn_variant", C.c_int32),
-        ("reserved", C.c_int32),
+        ("shard_mode", C.c_int32),
     ]
 
 

@@ -1120,7 +1120,9 @@ int enqueue_nn(icp_handle* h, long long n_q)
     rc = h->surface ? launch_nn_surface(h, n_q)
                     : (h->prm.nn_mode == ICP_NN_BVH ? launch_nn_bvh(h, n_q) : launch_nn(h, n_q));
     if (rc) return rc;
-    if (h->prm.world_size > 1 && n_q > 0) {
+    if (h->prm.world_size > 1 && h->prm.shard_mode == ICP_SHARD_QUERIES && h->prm.reject_fraction > 0)
+        return fail(h, ICP_ERR_BAD_ARG, "reject_fraction needs every query on every rank: use ICP_SHARD_BASE");
+    if (h->prm.world_size > 1 && h->prm.shard_mode == ICP_SHARD_BASE && n_q > 0) {
         if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
         ProfScope ps(h, 4);
         NCCL_TRY(h, g_nccl.AllReduce(h->d_keys, h->d_keys, (size_t)n_q, ncclUint64, ncclMin, h->comm,
@@ -1195,10 +1197,19 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     {
         ProfScope ps(h, 2);
         k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
+        h->launches += 1;
+    }
+    if (h->prm.world_size > 1) {      // queries sharded: the only exchange is the 20-double moment sum
+        if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
+        ProfScope ps(h, 4);
+        NCCL_TRY(h, g_nccl.AllReduce(h->d_moments, h->d_moments, MOM, ncclDouble, ncclSum, h->comm, h->stream));
+    }
+    {
+        ProfScope ps(h, 2);
         k_solve_update<<<1, 32, 0, h->stream>>>(h->d_state, h->d_moments, h->prm.align_meth == 1,
                                                 h->prm.use_target, h->prm.target_d, h->d_stats,
                                                 h->stats_capacity);
-        h->launches += 2;
+        h->launches += 1;
     }
     CUDA_TRY(h, cudaGetLastError());
     return ICP_OK;
@@ -1206,7 +1217,8 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
 
 int enqueue_iteration(icp_handle* h, long long n_q)
 {
-    if (h->prm.nn_mode == ICP_NN_BVH && h->prm.world_size == 1 && !(h->prm.reject_fraction > 0) &&
+    if (h->prm.nn_mode == ICP_NN_BVH && (h->prm.world_size == 1 || h->prm.shard_mode == ICP_SHARD_QUERIES) &&
+        !(h->prm.reject_fraction > 0) &&
         h->prm.nn_variant != 10 && h->prm.nn_variant != 11 && h->prm.nn_variant != 99 && h->prm.nn_variant != 98)
         return enqueue_iteration_fused(h, n_q);
     int rc = enqueue_nn(h, n_q);
@@ -1499,19 +1511,19 @@ int icp_set_moving(icp_handle* h, const float* xyz, int64_t n_vertices, const in
     h->warm_valid = false;
     h->has_vlist = vlist != nullptr;
     h->n_vlist = n_vlist;
+    // moments are accumulated about the first vertex of the (replicated) moving array, so that
+    // every rank of a query-sharded run uses the same reference point
     double shift[3] = {0, 0, 0};
+    if (n_vertices > 0)
+        for (int k = 0; k < 3; ++k) shift[k] = xyz[k];
     if (vlist) {
         for (int64_t i = 0; i < n_vlist; ++i)
             if (vlist[i] < 0 || vlist[i] >= n_vertices)
                 return fail(h, ICP_ERR_BAD_ARG, "icp_set_moving: vlist[%lld] = %d out of range", (long long)i, vlist[i]);
         rc = ensure(h, h->d_vlist, h->vlist_capacity, n_vlist);
         if (rc) return rc;
-        if (n_vlist > 0) {
+        if (n_vlist > 0)
             CUDA_TRY(h, cudaMemcpyAsync(h->d_vlist, vlist, (size_t)n_vlist * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-            for (int k = 0; k < 3; ++k) shift[k] = xyz[3 * (int64_t)vlist[0] + k];
-        }
-    } else if (n_vertices > 0) {
-        for (int k = 0; k < 3; ++k) shift[k] = xyz[k];
     }
     CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, shift), shift, sizeof(shift), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1601,7 +1613,7 @@ int icp_make_pairs(icp_handle* h, int calc_stats, double* A, double* B, int64_t 
 {
     int rc = check_ready(h);
     if (rc) return rc;
-    if (h->prm.world_size > 1)
+    if (h->prm.world_size > 1 && h->prm.shard_mode == ICP_SHARD_BASE)
         return fail(h, ICP_ERR_STATE, "icp_make_pairs materialises pairs on one GPU; use icp_step/icp_run with sharded bases");
     if (!pairs_out) return fail(h, ICP_ERR_BAD_ARG, "icp_make_pairs: pairs_out is null");
     CUDA_TRY(h, cudaSetDevice(h->prm.device));

@@ -67,12 +67,13 @@ class IcpEngine:
 
     def __init__(self, *, thresh=0.5, target_d=0.01, use_target=True, align_meth="0", stride=1,
                  reject_fraction=0.0, device=0, rank=0, world_size=1, nn_mode=N.NN_BRUTEFORCE,
-                 nn_variant=0):
+                 nn_variant=0, shard_mode=N.SHARD_BASE):
         self._lib = N.lib()
         self._h = C.c_void_p()
         self.params = N.IcpParams()
         self._fill_params(thresh, target_d, use_target, align_meth, stride, reject_fraction,
                           device, rank, world_size, nn_mode, nn_variant)
+        self.params.shard_mode = int(shard_mode)
         rc = self._lib.icp_create(C.byref(self.params), C.byref(self._h))
         if rc != N.ICP_OK:
             msg = self._lib.icp_last_error(None).decode()
@@ -165,6 +166,17 @@ class IcpEngine:
                                                  vlist.ctypes.data, vlist.shape[0]))
         else:
             self._check(self._lib.icp_set_moving(self._h, xyz.ctypes.data, xyz.shape[0], None, 0))
+
+    def set_moving_sharded(self, xyz, vlist=None):
+        """ICP_SHARD_QUERIES: this rank keeps only its contiguous slice of the sampled query
+        positions (the stride is applied here, once, so every rank samples the same vertices)."""
+        xyz = _f32c(xyz, (-1, 3))
+        pos = np.arange(xyz.shape[0], dtype=np.int32) if vlist is None else np.ascontiguousarray(vlist, np.int32)
+        stride = self.params.stride if self.params.stride > 1 else 1
+        pos = pos[0::stride]
+        lo, hi = shard_range(pos.shape[0], self.params.rank, self.params.world_size)
+        self.update_params(stride=1)
+        self.set_moving(xyz, pos[lo:hi])
 
     def set_matrices(self, mw_align, mw_base):
         a = _f32c(mw_align, (4, 4))
