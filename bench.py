@@ -348,19 +348,31 @@ def run_ours(args, rank, world, local_rank):
         line_roofline = bvh_roofline(m // (world if shard_q else 1), n_local, nn_avg_ms, hbm_peak_of(peaks), args.workload)
         if surface:
             line_roofline["kernel"] = "k_nn_surface"
+    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    pairs_per_s = m * n_local / (nn_avg_ms * 1e-3) if nn_avg_ms > 0 else 0.0
+    cyc_per_pair = 148 * 4 * 32 * sm_hz * 1e6 / pairs_per_s if pairs_per_s else None
     roofline = line_roofline if nn_mode != 0 else {
-        "kernel": "k_nn_bruteforce_filter<4,3>" if (args.nn_variant in (0, 20) and n_local >= 262144) else "k_nn_bruteforce",
+        "kernel": bruteforce_kernel_name(args.nn_variant, n_local),
         "bound": "fp32",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "traffic": traffic,
         "peak_source": "FFMA/FFMA2 micro-benchmark measured in this run (icp_measure_fp32_peak); "
                        "MEASURED_PEAKS.json has no fp32 CUDA-core figure",
         "algorithmic": "8 FLOP x M_eff x N_local pair evaluations per launch (SURVEY 8d)",
-        "pairs_per_s": m * n_local / (nn_avg_ms * 1e-3), "avg_launch_ms": nn_avg_ms,
+        "pairs_per_s": pairs_per_s, "avg_launch_ms": nn_avg_ms,
         "share_of_step": nn_ms / sum(step_ms),
+        # the lower-bound kernels execute fewer flops than the algorithmic 8 per pair, so `frac` can
+        # exceed 1; what binds them is the issue rate: on sm_100a every 3-register fp32 warp
+        # instruction (FFMA2, FMNMX3) holds its scheduler for 2 cycles (tools/ubench/pipes.cu)
+        "issue_model": {"sm_cycles_per_pair_lane": cyc_per_pair,
+                        "floor_cycles_per_pair": BRUTEFORCE_FLOOR.get(bruteforce_kernel_name(args.nn_variant, n_local).split("<")[0]),
+                        "note": "floor = 2 cycles x (FFMA2 + FMNMX3 warp instructions per pair): direct 3.5, "
+                                "expansion filter 2.0, cylinder filter 1.5 instructions per pair"},
         "why_not_hbm": "brute-force NN is fp32-issue bound: %.0f MB compulsory traffic per iteration vs "
                        "%.1e pair evaluations (SURVEY D4)" % ((12 * n_local + 52 * m) / 1e6, float(m) * n_local),
     }
+    if nn_mode == 0 and roofline["issue_model"]["floor_cycles_per_pair"] and cyc_per_pair:
+        roofline["issue_model"]["frac_of_floor"] = roofline["issue_model"]["floor_cycles_per_pair"] / cyc_per_pair
     stream_bytes = 12.0 * n_local + 52.0 * m
     hbm_peak = hbm_peak_of(peaks)
     mom_avg_ms = mom_ms / max(mom_launches, 1)
@@ -410,6 +422,21 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu_baseline(cfg, args.cpu_sample, 2)
         line["cpu_fair"] = cpu_fair_comparator(cfg)
     print(json.dumps(line), flush=True)
+
+
+BRUTEFORCE_FLOOR = {"k_nn_bruteforce": 7.0, "k_nn_bruteforce_filter": 4.0, "k_nn_bruteforce_cyl": 3.0}
+
+
+def bruteforce_kernel_name(variant, n_local):
+    """The K2 kernel the library picks for the timed (seeded) passes (icp_b200.cu launch_nn)."""
+    tiles = (n_local + 1023) // 1024
+    if variant == 0:
+        return "k_nn_bruteforce_cyl<4,3,32>" if tiles >= 16 else "k_nn_bruteforce<4,4,1>"
+    if 30 <= variant <= 36:
+        return "k_nn_bruteforce_cyl"
+    if 20 <= variant <= 29:
+        return "k_nn_bruteforce_filter"
+    return "k_nn_bruteforce"
 
 
 def hbm_peak_of(peaks):

@@ -30,6 +30,7 @@
 #include "device_math.cuh"
 #include "icp_state.cuh"
 #include "nn_bruteforce.cuh"
+#include "nn_bruteforce_cyl.cuh"
 #include "nn_bvh.cuh"
 #include "nn_surface.cuh"
 
@@ -68,14 +69,15 @@ __global__ void k_build_base(const float* __restrict__ xyz, long long n, long lo
 // K1: sampled vertex -> base-local query (two S1 products), SoA out, one query per SLOT.
 // slot_pos (nullable = identity) maps a slot to its query position: slots are the Morton order
 // of the moving vertices, so that neighbouring threads of the tree search walk the same nodes.
-// Keys are reset to "none" -- or, with `warm`, to the previous iteration's winner re-evaluated
-// under the new pose: a real base vertex, hence a valid candidate and a tight initial bound.
+// Keys are reset to "none" -- or, with `warm_src`, to the previous pass's LOCAL winner re-evaluated
+// under the new pose: a real base vertex, hence a valid candidate and a tight initial bound
+// (tree searches prune with it; the brute-force filter kernel starts its running minimum from it).
 __global__ void k_transform_queries(const DevState* __restrict__ st, const float* __restrict__ mov,
                                     const int* __restrict__ vlist, int stride, long long n_q,
                                     const uint32_t* __restrict__ slot_pos,
                                     float* __restrict__ qx, float* __restrict__ qy,
-                                    float* __restrict__ qz, unsigned long long* __restrict__ keys,
-                                    int warm, const float4* __restrict__ base4,
+                                    float* __restrict__ qz, unsigned long long* keys,
+                                    const unsigned long long* warm_src, const float4* __restrict__ base4,
                                     const float4* __restrict__ tris4, long long base_off,
                                     long long n_local)
 {
@@ -90,8 +92,8 @@ __global__ void k_transform_queries(const DevState* __restrict__ st, const float
     s1_matvec(st->imx2, wx, wy, wz, x, y, z);
     qx[t] = x; qy[t] = y; qz[t] = z;
     unsigned long long key = KEY_NONE;
-    if (warm) {
-        const unsigned long long old = keys[t];
+    if (warm_src) {                                        // may alias keys (same element only)
+        const unsigned long long old = warm_src[t];
         const long long j = (long long)(uint32_t)(old & 0xFFFFFFFFull) - base_off;
         if (old != KEY_NONE && j >= 0 && j < n_local) {
             float d;
@@ -657,6 +659,12 @@ struct icp_handle {
     float* d_filter_tiles = nullptr;
     FilterInfo* d_filter_info = nullptr;
     bool filter_built = false;
+    // cylinder-filter tiles (nn_variant 30..): Morton-ordered, centred per tile, built lazily
+    float* d_cyl_ftiles = nullptr;         // [tile][a'|b'|w2|c'][1024]
+    float* d_cyl_etiles = nullptr;         // [tile][x|y|z|original index][1024]
+    CylTileHdr* d_cyl_hdrs = nullptr;
+    int cyl_axes = 0;                      // a | b << 2 | c << 4
+    int cyl_sorted = -1;                   // how the current tiles were built (-1: not built)
     // spatial index (nn_mode == ICP_NN_BVH), built lazily from d_base4
     BvhNode* d_bvh_nodes = nullptr;
     float4* d_bvh_sorted = nullptr;
@@ -672,6 +680,13 @@ struct icp_handle {
     bool order_valid = false;
     int order_stride = 0;
     bool warm_valid = false;       // d_keys hold last iteration's winners for the current slots
+    // brute-force warm start: the previous pass's winners (this rank's own, before the shard
+    // resolution) seed the filter kernel's running minimum
+    bool bf_warm_valid = false;
+    bool bf_warm_active = false;   // the pass being enqueued was seeded
+    long long bf_warm_nq = 0;
+    unsigned long long* d_keys_local = nullptr;
+    long long keys_local_capacity = 0;
     // moving
     float* d_mov = nullptr;
     long long mov_capacity = 0, n_vertices = 0;
@@ -753,7 +768,24 @@ int ensure(icp_handle* h, T*& ptr, long long& cap, long long need)
     return ICP_OK;
 }
 
-bool uses_slots(const icp_handle* h) { return h->prm.nn_mode != ICP_NN_BRUTEFORCE; }
+// brute-force variants.  0 (default): query slots in Morton order; the unseeded first pass runs the
+// expansion-filter kernel (or the direct kernel on small shards), every later pass the cylinder
+// kernel over Morton-ordered, per-tile-centred base tiles, seeded with the previous winners.
+// 1..6 direct metric, 20..24 expansion filter, 30..36 cylinder filter on every pass:
+// 30 = sorted base + sorted query slots, 31 = base in its own order, 32 = queries in their own
+// order, 33 = neither, 34..36 = 30 with other blockings (8 queries/thread, 32-vertex chunks, both).
+bool cyl_variant(int v) { return v >= 30 && v <= 36; }
+bool cyl_sorts_base(const icp_handle* h)
+{
+    const int v = h->prm.nn_variant;
+    return v == 0 || v >= 34 || !(v & 1);
+}
+bool uses_slots(const icp_handle* h)
+{
+    if (h->prm.nn_mode != ICP_NN_BRUTEFORCE) return true;
+    const int v = h->prm.nn_variant;
+    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36);
+}
 
 long long query_count(const icp_handle* h)
 {
@@ -879,7 +911,92 @@ int launch_nn_filter_t(icp_handle* h, long long n_q)
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_filter_tiles, h->d_base_tiles, h->d_filter_info, h->n_tiles,
                                                 tiles_per_cta, qx, qy, qz, n_q, h->d_keys, (uint32_t)h->base_off,
-                                                &h->d_state->converged);
+                                                h->bf_warm_active ? 1 : 0, &h->d_state->converged);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+int build_cyl(icp_handle* h)
+{
+    const int want_sorted = cyl_sorts_base(h) ? 1 : 0;
+    if (h->cyl_sorted == want_sorted) return ICP_OK;
+    for (void* p : {(void*)h->d_cyl_ftiles, (void*)h->d_cyl_etiles, (void*)h->d_cyl_hdrs}) if (p) cudaFree(p);
+    h->d_cyl_ftiles = h->d_cyl_etiles = nullptr; h->d_cyl_hdrs = nullptr;
+    const long long n = h->n_local;
+    if (n > 0) {
+        unsigned long long *codes = nullptr, *codes_out = nullptr;
+        uint32_t *order = nullptr, *order_out = nullptr;
+        float *part = nullptr, *bbox = nullptr;
+        void* temp = nullptr;
+        size_t temp_bytes = 0;
+        const int pb = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
+        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 24));
+        CUDA_TRY(h, cudaMalloc((void**)&bbox, 24));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_cyl_ftiles, (size_t)h->n_tiles * CYL_TILE_BYTES));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_cyl_etiles, (size_t)h->n_tiles * CYL_TILE_BYTES));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_cyl_hdrs, (size_t)h->n_tiles * sizeof(CylTileHdr)));
+        k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
+        k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+        h->launches += 2;
+        if (want_sorted) {
+            CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n * 8));
+            CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n * 8));
+            CUDA_TRY(h, cudaMalloc((void**)&order, (size_t)n * 4));
+            CUDA_TRY(h, cudaMalloc((void**)&order_out, (size_t)n * 4));
+            k_morton_codes<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order);
+            CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
+            CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+            CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
+            h->launches += 2;
+        }
+        // the dropped axis c is the one of smallest extent: the lower bound loses the least there
+        float hb[6];
+        CUDA_TRY(h, cudaMemcpyAsync(hb, bbox, 24, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        int c = 2;
+        float ext[3];
+        for (int k = 0; k < 3; ++k) { ext[k] = hb[3 + k] - hb[k]; if (!(ext[k] >= 0.0f)) ext[k] = 0.0f; }
+        for (int k = 1; k >= 0; --k) if (ext[k] < ext[c]) c = k;
+        const int a = (c + 1) % 3, b = (c + 2) % 3;
+        h->cyl_axes = a | (b << 2) | (c << 4);
+        k_build_cyl_tiles<<<(unsigned)h->n_tiles, 256, 0, h->stream>>>(h->d_base4, want_sorted ? order_out : nullptr, n, a, b, c,
+                                                                      h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs);
+        h->launches += 1;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (void* p : {(void*)codes, (void*)codes_out, (void*)order, (void*)order_out, (void*)part, (void*)bbox, temp}) if (p) cudaFree(p);
+    }
+    h->cyl_sorted = want_sorted;
+    return ICP_OK;
+}
+
+template <int R, int STAGES, int CH>
+int launch_nn_cyl_t(icp_handle* h, long long n_q)
+{
+    auto kern = k_nn_bruteforce_cyl<R, STAGES, CH>;
+    const size_t smem = (size_t)STAGES * CYL_TILE_BYTES + STAGES * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)h->sm_count * occ;
+    long long want_y = (8 * slots + qb - 1) / qb;
+    long long max_y = std::max<long long>(1, h->n_tiles / 8);
+    long long gy = std::max<long long>(1, std::min(want_y, max_y));
+    int tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy);
+    gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    if (gy > 65535) { gy = 65535; tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy); gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta; }
+    dim3 grid((unsigned)qb, (unsigned)gy);
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->cyl_axes, h->n_tiles,
+                                                tiles_per_cta, qx, qy, qz, n_q, h->d_keys, (uint32_t)h->base_off,
+                                                h->bf_warm_active ? 1 : 0, &h->d_state->converged);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return ICP_OK;
@@ -888,16 +1005,25 @@ int launch_nn_filter_t(icp_handle* h, long long n_q)
 int launch_nn(icp_handle* h, long long n_q)
 {
     if (n_q <= 0 || h->n_tiles <= 0) return ICP_OK;
-    // default (variant 0): the expansion-filter kernel once every CTA scans enough chunks for its
-    // slow path to be rare (>= 256 tiles = 262k base vertices per shard), the direct kernel below
     int variant = h->prm.nn_variant;
-    if (variant == 0) variant = (h->n_tiles >= 256) ? 20 : 2;
+    if (variant == 0) {
+        if (h->bf_warm_active && h->n_tiles >= 16) variant = 35;       // seeded: cylinder kernel
+        else variant = h->n_tiles >= 256 ? 20 : 2;                     // cold: filter / direct kernel
+    }
     if (variant >= 20 && variant <= 29) {
         int rc = build_filter(h);      // outside the profiled region (one-time)
         if (rc) return rc;
     }
+    if (cyl_variant(variant)) {
+        int rc = build_cyl(h);
+        if (rc) return rc;
+    }
     ProfScope ps(h, 0);
     switch (variant) {
+        case 30: case 31: case 32: case 33: return launch_nn_cyl_t<4, 3, 16>(h, n_q);
+        case 34: return launch_nn_cyl_t<8, 3, 16>(h, n_q);
+        case 35: return launch_nn_cyl_t<4, 3, 32>(h, n_q);
+        case 36: return launch_nn_cyl_t<8, 3, 32>(h, n_q);
         case 20: return launch_nn_filter_t<4, 3>(h, n_q);   // expansion filter + exact re-check
         case 21: return launch_nn_filter_t<8, 3>(h, n_q);
         case 22: return launch_nn_filter_t<4, 4>(h, n_q);
@@ -1062,6 +1188,7 @@ int ensure_query_buffers(icp_handle* h, long long n_q)
         if (h->d_q) cudaFree(h->d_q);
         if (h->d_keys) cudaFree(h->d_keys);
         h->d_q = nullptr; h->d_keys = nullptr; h->q_capacity = 0;
+        h->warm_valid = false; h->bf_warm_valid = false;
         const long long cap = std::max<long long>(n_q, 1);
         CUDA_TRY(h, cudaMalloc((void**)&h->d_q, (size_t)cap * 3 * sizeof(float)));
         CUDA_TRY(h, cudaMalloc((void**)&h->d_keys, (size_t)cap * sizeof(unsigned long long)));
@@ -1097,21 +1224,33 @@ int enqueue_nn(icp_handle* h, long long n_q)
     if (rc) return rc;
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
-    const bool bvh = uses_slots(h);      // BVH and surface modes: Morton-ordered slots + warm start
-    if (bvh) {
+    const bool slots = uses_slots(h);    // Morton-ordered query slots (tree searches, sorted brute force)
+    const bool tree = h->prm.nn_mode != ICP_NN_BRUTEFORCE;
+    const bool sharded_base = h->prm.world_size > 1 && h->prm.shard_mode == ICP_SHARD_BASE;
+    const unsigned long long* warm_src = nullptr;
+    if (slots) {
         rc = ensure_query_order(h, n_q);
         if (rc) return rc;
+    }
+    if (tree) {
+        if (h->warm_valid) warm_src = h->d_keys;
     } else {
         h->warm_valid = false;
+        // brute force: any real local vertex is a valid seed, so the previous winners stay usable
+        // for as long as the base and the query count are unchanged (a new pose or new moving
+        // coordinates only change how tight the seed is)
+        if (h->bf_warm_valid && h->bf_warm_nq == n_q && h->prm.nn_variant != 1 && n_q > 0)
+            warm_src = sharded_base ? h->d_keys_local : h->d_keys;
     }
+    h->bf_warm_active = !tree && warm_src != nullptr;
     {
         ProfScope ps(h, 3);
         k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
         if (n_q > 0)
             k_transform_queries<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(
                 h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q,
-                bvh ? h->d_slot_pos : nullptr, qx, qy, qz, h->d_keys,
-                (bvh && h->warm_valid) ? 1 : 0, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off,
+                slots ? h->d_slot_pos : nullptr, qx, qy, qz, h->d_keys,
+                warm_src, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off,
                 h->n_local);
         h->launches += 2;
     }
@@ -1122,20 +1261,28 @@ int enqueue_nn(icp_handle* h, long long n_q)
     if (rc) return rc;
     if (h->prm.world_size > 1 && h->prm.shard_mode == ICP_SHARD_QUERIES && h->prm.reject_fraction > 0)
         return fail(h, ICP_ERR_BAD_ARG, "reject_fraction needs every query on every rank: use ICP_SHARD_BASE");
-    if (h->prm.world_size > 1 && h->prm.shard_mode == ICP_SHARD_BASE && n_q > 0) {
+    if (sharded_base && n_q > 0) {
         if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
         ProfScope ps(h, 4);
+        if (!tree) {       // keep this rank's own winners: they seed the next pass
+            rc = ensure(h, h->d_keys_local, h->keys_local_capacity, n_q);
+            if (rc) return rc;
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_keys_local, h->d_keys, (size_t)n_q * sizeof(unsigned long long),
+                                        cudaMemcpyDeviceToDevice, h->stream));
+        }
         NCCL_TRY(h, g_nccl.AllReduce(h->d_keys, h->d_keys, (size_t)n_q, ncclUint64, ncclMin, h->comm,
                                      h->stream));
     }
-    h->warm_valid = bvh;          // d_keys now hold this pass's winners, slot-aligned
+    h->warm_valid = tree;         // d_keys now hold this pass's winners, slot-aligned
+    h->bf_warm_valid = !tree && n_q > 0;
+    h->bf_warm_nq = n_q;
     if (h->prm.reject_fraction > 0 && n_q > 0) {
         ProfScope ps(h, 1);
         const long long keep = n_q - (long long)std::floor(h->prm.reject_fraction * (double)n_q);
         k_select_init<<<1, 256, 0, h->stream>>>(h->d_state, keep - 1, h->d_hist);
         const int g = (int)std::min<long long>((n_q + 255) / 256, (long long)h->sm_count * 8);
         for (int byte = 7; byte >= 0; --byte) {
-            k_select_hist<<<g, 256, 0, h->stream>>>(h->d_state, h->d_keys, bvh ? h->d_slot_pos : nullptr, n_q, byte, h->d_hist);
+            k_select_hist<<<g, 256, 0, h->stream>>>(h->d_state, h->d_keys, slots ? h->d_slot_pos : nullptr, n_q, byte, h->d_hist);
             k_select_pick<<<1, 256, 0, h->stream>>>(h->d_state, byte, h->d_hist);
         }
         h->launches += 17;
@@ -1194,6 +1341,7 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
         h->launches += 1;
     }
     h->warm_valid = true;
+    h->bf_warm_valid = false;
     {
         ProfScope ps(h, 2);
         k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
@@ -1373,7 +1521,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1409,7 +1557,9 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
     h->surface = false;
     h->bvh_built = false;
     h->filter_built = false;
+    h->cyl_sorted = -1;
     h->warm_valid = false;
+    h->bf_warm_valid = false;
     if (n_local > 0) {
         float* d_raw = nullptr;
         CUDA_TRY(h, cudaMalloc((void**)&h->d_base_tiles, (size_t)n_pad * 3 * sizeof(float)));
@@ -1438,7 +1588,7 @@ int icp_set_base_triangles(icp_handle* h, const float* tri_xyz, int64_t n_local,
     h->n_local = n_local; h->n_global = n_global; h->base_off = global_offset;
     h->n_tiles = 0;
     h->surface = true;
-    h->bvh_built = false; h->filter_built = false; h->warm_valid = false;
+    h->bvh_built = false; h->filter_built = false; h->warm_valid = false; h->bf_warm_valid = false;
     h->tri_runs = 0; h->tri_extent = 0.0f;
     if (n_local > 0) {
         const long long n = n_local;

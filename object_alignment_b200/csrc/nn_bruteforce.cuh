@@ -303,7 +303,7 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
                        const FilterInfo* __restrict__ info, int n_tiles, int tiles_per_cta,
                        const float* __restrict__ qx, const float* __restrict__ qy,
                        const float* __restrict__ qz, long long n_queries,
-                       unsigned long long* __restrict__ keys, uint32_t index_offset,
+                       unsigned long long* __restrict__ keys, uint32_t index_offset, int seeded,
                        const int* __restrict__ stop_flag)
 {
     if (stop_flag != nullptr && *stop_flag != 0) return;
@@ -350,6 +350,19 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
         delta[r] = 2.0e-6f * s * s;
         be[r] = inf; bed[r] = inf;
         bkey[r] = KEY_NONE;
+        if (seeded && ok) {
+            // keys[p] already names a real vertex j of THIS shard (K1 re-evaluated the previous
+            // winner; other CTAs may have lowered it since -- still a real vertex).  The shard
+            // winner j* satisfies E(j*) <= E(j) + delta for every j of the shard, wherever j lies,
+            // so E(j) is a valid starting value of the running minimum.
+            const unsigned long long k0 = *reinterpret_cast<const volatile unsigned long long*>(&keys[p]);
+            const long long j = (long long)(uint32_t)(k0 & 0xFFFFFFFFull) - (long long)index_offset;
+            if (k0 != KEY_NONE && j >= 0 && j < (long long)n_tiles * NN_TILE) {
+                const float* t = ftiles + (j / NN_TILE) * (NN_TILE * 4) + (j % NN_TILE);
+                const float e = __fmaf_rn(az, t[2 * NN_TILE], __fmaf_rn(ay, t[NN_TILE], __fmaf_rn(ax, t[0], t[3 * NN_TILE])));
+                if (e < inf) { be[r] = e; bed[r] = e + delta[r]; }
+            }
+        }
     }
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -386,7 +399,10 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
 #pragma unroll
             for (int r = 0; r < R; ++r) trig = trig || (cm[r] <= bed[r]);
             if (trig) {
-                // slow path: exact S4 on the candidates of this chunk
+                // slow path: exact S4 on the candidates of this chunk.  Kept INLINE on purpose: with it
+                // ptxas routes the tile operands of the hot loop through uniform registers (R2UR), and
+                // FFMA2 with a uniform operand avoids the register-bank dispatch stalls of the
+                // all-register form (measured: 116 ms inline vs 136 ms out of line at 1M x 1M)
                 const long long jbase = ((long long)(t0 + it)) * NN_TILE + (long long)c * NN_CHUNK;
                 const float* gp = base_tiles + (long long)(t0 + it) * (NN_TILE * 3) + c * NN_CHUNK;
                 const float* fx = tile + c * NN_CHUNK;

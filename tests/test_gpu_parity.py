@@ -17,7 +17,7 @@ from tests.golden_util import GOLDEN, Golden, scenario_names
 
 pytestmark = pytest.mark.gpu
 
-NN_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 20, 21, 22, 23, 24]
+NN_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 20, 21, 22, 23, 24, 30, 31, 32, 33, 34, 35, 36]
 
 
 def _rand_cloud(n, seed, scale=1.0):
@@ -94,7 +94,7 @@ def test_nn_vlist_stride_and_matrices():
         assert np.array_equal(d2.view(np.uint32), res["d2"].view(np.uint32))
 
 
-@pytest.mark.parametrize("variant", [20, 21])
+@pytest.mark.parametrize("variant", [20, 21, 30, 33, 35, 36])
 @pytest.mark.parametrize("case", ["surface", "far_outliers", "duplicates", "collinear", "volume", "lattice",
                                   "far_from_origin", "sorted_base"])
 def test_filter_kernel_matches_oracle(case, variant):
@@ -123,13 +123,16 @@ def test_filter_kernel_matches_oracle(case, variant):
 def test_filter_kernel_equals_direct_kernel_at_1m():
     cfg = meshgen.config_cloud(1_000_000, 1_000_000, 200, 201)
     res = {}
-    for variant in (0, 20):
+    for variant in (2, 20, 35, 0):
         with IcpEngine(nn_variant=variant) as e:
             e.set_base(cfg["base"])
             e.set_moving(cfg["moving"])
             e.set_matrices(np.eye(4), np.eye(4))
             res[variant] = e.nn()
-    assert np.array_equal(res[0][0], res[20][0]) and np.array_equal(res[0][1], res[20][1])
+            if variant == 0:
+                res["seeded"] = e.nn()           # second pass: seeded cylinder kernel
+    for other in (20, 35, 0, "seeded"):
+        assert np.array_equal(res[2][0], res[other][0]) and np.array_equal(res[2][1], res[other][1])
 
 
 def test_nn_100k_vs_100k_c2():
@@ -413,6 +416,56 @@ def test_bvh_warm_start_stays_exact_over_iterations():
             M, st = e.step()
             assert st.pairs == int(res["keep"].sum())
             np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(res["A"], res["B"]), atol=1e-10)
+
+
+@pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36])
+def test_bruteforce_seeded_passes_stay_exact(variant):
+    """From the second pass on the brute-force filter kernel starts its running minimum from the
+    previous winner re-evaluated under the new pose.  Every pass must still return the oracle's
+    keys: over converging iterations, after a wild pose jump (useless seeds), after the moving
+    vertices are replaced by unrelated ones of the same count (stale seeds), and on a lattice
+    where the seed becomes a higher-index TIE of the new winner."""
+    cfg = meshgen.config_cloud(30_000, 80_000, 71, 72)
+    n_mov = cfg["moving"].shape[0]
+    with IcpEngine(thresh=0.5, use_target=False, nn_variant=variant) as e:
+        e.set_base(cfg["base"])
+        e.set_moving(cfg["moving"])
+        e.set_matrices(np.eye(4), np.eye(4))
+        for it in range(5):
+            mw = e.matrix_world()
+            res = orc.make_pairs_vec(cfg["moving"], np.arange(n_mov), mw, np.eye(4), cfg["base"], 0.5, 1,
+                                     return_all=True, nn="kdtree")
+            idx, d2 = e.nn()
+            assert np.array_equal(idx, res["idx"]) and np.array_equal(d2, res["d2"])
+            M, st = e.step()                                        # seeded as well
+            assert st.pairs == int(res["keep"].sum())
+        jump = meshgen.rigid_matrix(171.0, (0.4, -0.3, 0.25), axis=(-1.0, 0.2, 0.4))
+        e.set_matrices(jump, np.eye(4))
+        res = orc.make_pairs_vec(cfg["moving"], np.arange(n_mov), jump, np.eye(4), cfg["base"], 1e9, 1,
+                                 return_all=True, nn="kdtree")
+        idx, d2 = e.nn()
+        assert np.array_equal(idx, res["idx"]) and np.array_equal(d2, res["d2"])
+        other = _rand_cloud(n_mov, 99, 0.7)
+        e.set_moving(other)
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+        oi, od = orc.nn_bruteforce(other, cfg["base"])
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # lattice: shift the pose by exactly one cell, the old winner is now a tie with a higher index
+    g = np.arange(28, dtype=np.float32)
+    base = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)     # 21952 vertices
+    mov = (base[::3] + np.float32(0.5)).astype(np.float32)
+    mov = mov[(mov < 26).all(axis=1)]
+    with IcpEngine(nn_variant=variant) as e:
+        e.set_base(base)
+        e.set_moving(mov)
+        for shift in ((0, 0, 0), (-1, 0, 0), (0, 1, 0), (0, 0, -1), (1, -1, 1)):
+            mw = np.eye(4, dtype=np.float32)
+            mw[:3, 3] = shift
+            e.set_matrices(mw, np.eye(4))
+            idx, d2 = e.nn()
+            oi, od = orc.nn_bruteforce((mov + np.array(shift, np.float32)).astype(np.float32), base)
+            assert np.array_equal(idx, oi) and np.array_equal(d2, od)
 
 
 def test_reference_shaped_loop_with_icp_step():
