@@ -283,20 +283,87 @@ k_filter_moments(const DevState* __restrict__ st, const float* __restrict__ mov,
                  const float* __restrict__ qz, const unsigned long long* __restrict__ keys,
                  const float4* __restrict__ base4, const float4* __restrict__ tris4, long long base_off,
                  long long n_local, double thresh, int use_select, const uint32_t* __restrict__ slot_pos,
-                 double* __restrict__ partials)
+                 const float4* __restrict__ mov_slots, double* __restrict__ partials)
 {
+    // mov_slots (nullable; present whenever slot_pos is): float4(moving vertex, query position bits) per
+    // slot, so the moving coordinates stream in slot order instead of being gathered through slot_pos.
     if (st->converged) return;
     double acc[MOM];
 #pragma unroll
     for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
     const double s0 = st->shift[0], s1 = st->shift[1], s2 = st->shift[2];
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_q;
-         t += (long long)gridDim.x * blockDim.x) {
-        const long long p = slot_pos ? (long long)slot_pos[t] : t;
-        const PairEval e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, tris4, base_off,
-                                     n_local, thresh, use_select, t, p);
-        if (!e.keep) continue;
-        moments_add(acc, e.ax, e.ay, e.az, e.bx, e.by, e.bz, e.dist, s0, s1, s2);
+    // Each CTA owns one contiguous, 32-aligned range of slots (balanced to within a warp), and each
+    // thread keeps MOM_BATCH queries in flight: the key -> winner-gather chain is two dependent DRAM
+    // round trips, so the loads of a batch are issued together, stage by stage, before any arithmetic.
+    const long long per = ((n_q + gridDim.x - 1) / gridDim.x + 31) & ~31ll;
+    const long long lo = (long long)blockIdx.x * per;
+    const long long hi = lo + per < n_q ? lo + per : n_q;
+    if (tris4 != nullptr) {             // surface mode: three gathers + region walk per pair, unbatched
+        for (long long t = lo + threadIdx.x; t < hi; t += MOM_THREADS) {
+            const long long p = slot_pos ? (long long)slot_pos[t] : t;
+            const PairEval e = eval_pair(st, mov, vlist, stride, qx, qy, qz, keys, base4, tris4, base_off,
+                                         n_local, thresh, use_select, t, p);
+            if (!e.keep) continue;
+            moments_add(acc, e.ax, e.ay, e.az, e.bx, e.by, e.bz, e.dist, s0, s1, s2);
+        }
+        block_reduce_moments<MOM_THREADS>(acc, partials);
+        return;
+    }
+    const bool sel_ok = use_select ? (st->sel_valid != 0) : true;
+    const unsigned long long sel_thr = use_select ? st->sel_threshold : ~0ull;
+    for (long long t0 = lo + threadIdx.x; t0 < hi; t0 += (long long)MOM_THREADS * MOM_BATCH) {
+        unsigned long long key[MOM_BATCH];
+        long long p[MOM_BATCH];
+        float x[MOM_BATCH], y[MOM_BATCH], z[MOM_BATCH];
+        float ax[MOM_BATCH], ay[MOM_BATCH], az[MOM_BATCH];
+        bool ok[MOM_BATCH];
+#pragma unroll
+        for (int k = 0; k < MOM_BATCH; ++k) {                 // stage 1: streaming loads
+            const long long t = t0 + (long long)k * MOM_THREADS;
+            ok[k] = t < hi;
+            key[k] = KEY_NONE; p[k] = t; x[k] = y[k] = z[k] = 0.0f;
+            ax[k] = ay[k] = az[k] = 0.0f;
+            if (ok[k]) {
+                key[k] = keys[t];
+                if (mov_slots) {
+                    const float4 a = mov_slots[t];
+                    ax[k] = a.x; ay[k] = a.y; az[k] = a.z;
+                    p[k] = (long long)__float_as_uint(a.w);
+                } else if (slot_pos) {
+                    p[k] = (long long)slot_pos[t];
+                }
+                x[k] = qx[t]; y[k] = qy[t]; z[k] = qz[t];
+            }
+        }
+        float4 co1[MOM_BATCH];
+#pragma unroll
+        for (int k = 0; k < MOM_BATCH; ++k) {                 // stage 2: gathers
+            const long long j = (long long)(uint32_t)(key[k] & 0xFFFFFFFFull) - base_off;
+            ok[k] = ok[k] && key[k] != KEY_NONE && j >= 0 && j < n_local;   // else another rank owns the target
+            if (use_select) {
+                const unsigned long long c = (key[k] & 0xFFFFFFFF00000000ull) | (unsigned long long)p[k];
+                ok[k] = ok[k] && sel_ok && c <= sel_thr;
+            }
+            co1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[k]) {
+                co1[k] = base4[j];
+                if (!mov_slots) {
+                    const long long vi = vlist ? (long long)vlist[p[k] * stride] : p[k] * stride;
+                    ax[k] = mov[3 * vi]; ay[k] = mov[3 * vi + 1]; az[k] = mov[3 * vi + 2];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MOM_BATCH; ++k) {                 // stage 3: general.py:299-306, in slot order
+            if (!ok[k]) continue;
+            float wqx, wqy, wqz, w1x, w1y, w1z, bx, by, bz;
+            s1_matvec(st->mw_base, x[k], y[k], z[k], wqx, wqy, wqz);
+            s1_matvec(st->mw_base, co1[k].x, co1[k].y, co1[k].z, w1x, w1y, w1z);
+            const double dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+            if (!(dist < thresh)) continue;                   // strict, general.py:302
+            s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);   // general.py:304
+            moments_add(acc, ax[k], ay[k], az[k], bx, by, bz, dist, s0, s1, s2);
+        }
     }
     block_reduce_moments<MOM_THREADS>(acc, partials);
 }
@@ -872,7 +939,7 @@ int build_filter(icp_handle* h)
         CUDA_TRY(h, cudaMalloc((void**)&bbox, 24));
         CUDA_TRY(h, cudaMalloc((void**)&h->d_filter_tiles, (size_t)n_pad * 4 * sizeof(float)));
         k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
-        k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+        k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
         k_filter_info<<<1, 32, 0, h->stream>>>(bbox, h->d_filter_info);
         k_build_filter_tiles<<<(unsigned)((n_pad + 255) / 256), 256, 0, h->stream>>>(h->d_base4, n, n_pad, h->d_filter_info, h->d_filter_tiles);
         h->launches += 4;
@@ -937,7 +1004,7 @@ int build_cyl(icp_handle* h)
         CUDA_TRY(h, cudaMalloc((void**)&h->d_cyl_etiles, (size_t)h->n_tiles * CYL_TILE_BYTES));
         CUDA_TRY(h, cudaMalloc((void**)&h->d_cyl_hdrs, (size_t)h->n_tiles * sizeof(CylTileHdr)));
         k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
-        k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+        k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
         h->launches += 2;
         if (want_sorted) {
             CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n * 8));
@@ -1068,7 +1135,7 @@ int build_bvh(icp_handle* h)
     CUDA_TRY(h, cudaMalloc((void**)&h->d_bvh_sorted, (size_t)n_pad * sizeof(float4)));
     CUDA_TRY(h, cudaMalloc((void**)&h->d_bvh_nodes, (size_t)std::max(1, n_runs - 1) * sizeof(BvhNode)));
     k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
-    k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+    k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
     k_morton_codes<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order);
     CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
     CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
@@ -1163,7 +1230,7 @@ int ensure_query_order(icp_handle* h, long long n_q)
         float* part = (float*)(sb + o_part);
         float* bbox = (float*)(sb + o_bbox);
         k_query_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_mov, vl, stride, n_q, part);
-        k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+        k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
         k_query_codes<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_mov, vl, stride, n_q, bbox, codes, pos);
         CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(sb + o_temp, temp_bytes, codes, codes_out, pos, h->d_slot_pos, (int)n_q, 0, 63, h->stream));
         k_invert_permutation<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_slot_pos, n_q, h->d_pos_slot);
@@ -1296,9 +1363,16 @@ int launch_nn_surface(icp_handle* h, long long n_q)
     if (n_q <= 0 || h->n_local <= 0) return ICP_OK;
     ProfScope ps(h, 0);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
-    k_nn_surface<<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz,
-                                                                      n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent,
-                                                                      &h->d_state->converged);
+    const unsigned g = (unsigned)((n_q + 127) / 128);
+    if (h->prm.nn_variant == 10) {       // per-thread walk (kept for A/B runs and as a cross-check)
+        k_nn_surface<<<g, 128, 0, h->stream>>>(h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz,
+                                               n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent,
+                                               &h->d_state->converged);
+    } else {                             // default: warp-packet walk
+        k_nn_surface_packet<false><<<g, PKT_THREADS, 0, h->stream>>>(
+            h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0,
+            n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent, nullptr);
+    }
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return ICP_OK;
@@ -1322,8 +1396,12 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     if (rc) return rc;
     rc = ensure_query_order(h, n_q);
     if (rc) return rc;
-    rc = build_bvh(h);
-    if (rc) return rc;
+    if (h->surface != (h->prm.nn_mode == ICP_NN_SURFACE))
+        return fail(h, ICP_ERR_STATE, "nn_mode ICP_NN_SURFACE needs icp_set_base_triangles (and the vertex modes need icp_set_base)");
+    if (!h->surface) {
+        rc = build_bvh(h);
+        if (rc) return rc;
+    }
     const int g = (int)std::max<long long>(1, (n_q + PKT_THREADS - 1) / PKT_THREADS);
     rc = ensure_partials(h, g);
     if (rc) return rc;
@@ -1334,10 +1412,16 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     }
     {
         ProfScope ps(h, 0);
-        k_nn_bvh_packet<true, false><<<g, PKT_THREADS, 0, h->stream>>>(
-            h->d_bvh_nodes, h->d_bvh_sorted, h->n_local > 0 ? h->bvh_P : 0, nullptr, nullptr, nullptr, h->d_state,
-            h->d_mov_slots, h->d_base4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
-            h->d_keys, (uint32_t)h->base_off, h->d_partials);
+        if (h->surface)
+            k_nn_surface_packet<true><<<g, PKT_THREADS, 0, h->stream>>>(
+                h->d_tri_nodes, h->d_tri_sorted, h->n_local > 0 ? h->tri_runs : 0, nullptr, nullptr, nullptr, h->d_state,
+                h->d_mov_slots, h->d_tris4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
+                h->d_keys, (uint32_t)h->base_off, h->tri_extent, h->d_partials);
+        else
+            k_nn_bvh_packet<true, false><<<g, PKT_THREADS, 0, h->stream>>>(
+                h->d_bvh_nodes, h->d_bvh_sorted, h->n_local > 0 ? h->bvh_P : 0, nullptr, nullptr, nullptr, h->d_state,
+                h->d_mov_slots, h->d_base4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
+                h->d_keys, (uint32_t)h->base_off, h->d_partials);
         h->launches += 1;
     }
     h->warm_valid = true;
@@ -1365,7 +1449,8 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
 
 int enqueue_iteration(icp_handle* h, long long n_q)
 {
-    if (h->prm.nn_mode == ICP_NN_BVH && (h->prm.world_size == 1 || h->prm.shard_mode == ICP_SHARD_QUERIES) &&
+    if ((h->prm.nn_mode == ICP_NN_BVH || h->prm.nn_mode == ICP_NN_SURFACE) &&
+        (h->prm.world_size == 1 || h->prm.shard_mode == ICP_SHARD_QUERIES) &&
         !(h->prm.reject_fraction > 0) &&
         h->prm.nn_variant != 10 && h->prm.nn_variant != 11 && h->prm.nn_variant != 99 && h->prm.nn_variant != 98)
         return enqueue_iteration_fused(h, n_q);
@@ -1380,7 +1465,7 @@ int enqueue_iteration(icp_handle* h, long long n_q)
             h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q, qx, qy, qz,
             h->d_keys, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off, h->n_local, h->prm.thresh,
             h->prm.reject_fraction > 0 ? 1 : 0,
-            uses_slots(h) ? h->d_slot_pos : nullptr, h->d_partials);
+            uses_slots(h) ? h->d_slot_pos : nullptr, uses_slots(h) ? h->d_mov_slots : nullptr, h->d_partials);
         k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
         h->launches += 2;
     }
@@ -1619,7 +1704,7 @@ int icp_set_base_triangles(icp_handle* h, const float* tri_xyz, int64_t n_local,
         k_tri_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_raw, n, h->d_tris4, cent);
         // bounding box over all triangle CORNERS (3n float4, stride 1) -> Morton grid + coordinate extent
         k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_tris4, 3 * n, part);
-        k_bbox_final<<<1, 32, 0, h->stream>>>(part, pb, bbox);
+        k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
         k_morton_codes<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(cent, n, bbox, codes, order);
         CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
         CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));

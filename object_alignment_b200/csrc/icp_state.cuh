@@ -8,6 +8,7 @@ namespace icp {
 // K, sum a'(3), sum b'(3), sum b' a'^T (9), sum|a'|^2, sum|b'|^2, sum d, sum d^2
 constexpr int MOM = 20;
 constexpr int MOM_THREADS = 256;
+constexpr int MOM_BATCH = 4;       // queries each k_filter_moments thread keeps in flight
 
 struct DevState {
     float mw_align[16];          // align_obj.matrix_world (updated every iteration, rule S3)

@@ -70,11 +70,17 @@ __global__ void k_bbox_partial(const float4* __restrict__ pts, long long n, floa
 }
 __global__ void k_bbox_final(const float* __restrict__ part, int n_part, float* __restrict__ bbox)
 {
-    const int k = threadIdx.x;
+    // one warp per component (launch with 6 * 32 threads)
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= 6) return;
-    float v = part[k];
-    for (int i = 1; i < n_part; ++i) v = (k < 3) ? fminf(v, part[i * 6 + k]) : fmaxf(v, part[i * 6 + k]);
-    bbox[k] = v;
+    const float inf = __int_as_float(0x7f800000);
+    float v = (k < 3) ? inf : -inf;
+    for (int i = lane; i < n_part; i += 32) v = (k < 3) ? fminf(v, part[i * 6 + k]) : fmaxf(v, part[i * 6 + k]);
+    for (int o = 16; o > 0; o >>= 1) {
+        const float w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (k < 3) ? fminf(v, w) : fmaxf(v, w);
+    }
+    if (lane == 0) bbox[k] = v;
 }
 
 __global__ void k_morton_codes(const float4* __restrict__ pts, long long n, const float* __restrict__ bbox,

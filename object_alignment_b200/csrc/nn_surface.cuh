@@ -223,4 +223,155 @@ k_nn_surface(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorte
     keys[p] = best;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-packet walk (default).  Query slots are in Morton order of the moving vertices, so the 32
+// queries of a warp are spatial neighbours: the warp walks the tree TOGETHER with one shared stack,
+// node and triangle loads are warp-uniform (one transaction, broadcast), every lane evaluates its
+// own bounds and its own S9/S10 distances, and a subtree is entered when ANY lane still needs it.
+// Each lane's prune test is exactly the per-thread kernel's, so the winner is the same key.  (The
+// per-thread walk diverges badly on a surface: ncu counted 4.3 active threads per warp instruction.)
+//
+// FUSED (one GPU or sharded queries, no percentile cut): the kernel also does K1 in its prologue
+// (q = imx2 @ (mx1 @ a), warm start = previous winning triangle re-evaluated under the new pose) and
+// K3+K4 in its epilogue (world distance, thresh, target = closest point on the winning triangle,
+// fp64 moment partials), so an ICP iteration is this kernel + one single-CTA solve.
+// ---------------------------------------------------------------------------------------------
+template <bool FUSED>
+__global__ void __launch_bounds__(PKT_THREADS)
+k_nn_surface_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
+                    const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
+                    const DevState* __restrict__ st, const float4* __restrict__ mov_slots,
+                    const float4* __restrict__ tris4, long long base_off, long long n_local, double thresh,
+                    int warm, long long n_queries, unsigned long long* __restrict__ keys,
+                    uint32_t index_offset, float coord_extent, double* __restrict__ partials)
+{
+    if (st->converged) return;
+    __shared__ int s_ref[PKT_THREADS / 32][BVH_STACK];
+    __shared__ float s_bound[PKT_THREADS / 32][BVH_STACK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < n_queries;
+    const float inf = __int_as_float(0x7f800000);
+
+    float x = 0.f, y = 0.f, z = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    float wx = 0.f, wy = 0.f, wz = 0.f;                 // closest point on the winner (FUSED epilogue)
+    unsigned long long best = KEY_NONE;
+    if (active) {
+        if (FUSED) {
+            const float4 a = mov_slots[t];
+            ax = a.x; ay = a.y; az = a.z;
+            float tx, ty, tz;
+            s1_matvec(st->mw_align, ax, ay, az, tx, ty, tz);
+            s1_matvec(st->imx2, tx, ty, tz, x, y, z);
+            if (warm) {
+                const unsigned long long old = keys[t];
+                const long long j = (long long)(uint32_t)(old & 0xFFFFFFFFull) - base_off;
+                if (old != KEY_NONE && j >= 0 && j < n_local) {
+                    const float4 a0 = tris4[3 * j], b0 = tris4[3 * j + 1], c0 = tris4[3 * j + 2];
+                    float rx, ry, rz;
+                    closest_on_tri(x, y, z, a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, c0.x, c0.y, c0.z, rx, ry, rz);
+                    const float d = s10_d2(x, y, z, rx, ry, rz);
+                    if (d < inf) {
+                        best = ((unsigned long long)__float_as_uint(d) << 32) | (old & 0xFFFFFFFFull);
+                        wx = rx; wy = ry; wz = rz;
+                    }
+                }
+            }
+        } else {
+            x = qx[t]; y = qy[t]; z = qz[t];
+            best = keys[t];
+        }
+    }
+    // S9 returns a point within ~eta of the triangle, so its distance can undercut the box bound by
+    // eta; prune in DISTANCE terms:  sqrt(bound) > sqrt(best) + eta          (same rule as k_nn_surface)
+    const float eta = 3.9e-6f * fmaxf(fmaxf(fabsf(x), fabsf(y)), fmaxf(fabsf(z), coord_extent));
+    float best_d = (best == KEY_NONE) ? inf : __uint_as_float((uint32_t)(best >> 32));
+    float prune_d = best_d + (2.0f * sqrtf(best_d) + eta) * eta;
+
+    int sp = 0;
+    int cur = (n_runs > 1) ? 0 : ~0;
+    const float4* nodes4 = reinterpret_cast<const float4*>(nodes);
+    if (n_runs > 0) {
+        while (true) {
+            if (cur < 0) {
+                const float4* lp = sorted + (long long)(~cur) * (TRI_LEAF * 3);
+#pragma unroll
+                for (int i = 0; i < TRI_LEAF; ++i) {
+                    const float4 a = __ldg(lp + 3 * i), b = __ldg(lp + 3 * i + 1), c = __ldg(lp + 3 * i + 2);
+                    if (a.x < inf) {                                        // warp-uniform (run padding)
+                        float rx, ry, rz;
+                        closest_on_tri(x, y, z, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, rx, ry, rz);
+                        const float d = s10_d2(x, y, z, rx, ry, rz);
+                        if (d <= best_d && d < inf && active) {
+                            const unsigned long long k =
+                                ((unsigned long long)__float_as_uint(d) << 32) |
+                                (unsigned long long)(index_offset + __float_as_uint(a.w));
+                            if (k < best) {
+                                best = k; best_d = d;
+                                prune_d = best_d + (2.0f * sqrtf(best_d) + eta) * eta;
+                                if (FUSED) { wx = rx; wy = ry; wz = rz; }
+                            }
+                        }
+                    }
+                }
+            } else {
+                const float4 n0 = __ldg(nodes4 + 4 * (long long)cur), n1 = __ldg(nodes4 + 4 * (long long)cur + 1);
+                const float4 n2 = __ldg(nodes4 + 4 * (long long)cur + 2), n3 = __ldg(nodes4 + 4 * (long long)cur + 3);
+                const float bl = box_lower_bound(x, y, z, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+                const float br = box_lower_bound(x, y, z, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+                const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+                const bool wl = active && !(bl * BVH_SHRINK > prune_d) && bl < inf;
+                const bool wr = active && !(br * BVH_SHRINK > prune_d) && br < inf;
+                const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
+                if (ml != 0u && mr != 0u) {
+                    const unsigned pl = __ballot_sync(0xffffffffu, wl && (!wr || bl <= br));
+                    const bool left_first = 2 * __popc(pl) >= __popc(ml | mr);
+                    const float fb = left_first ? (wr ? br : inf) : (wl ? bl : inf);
+                    const unsigned fmin = __reduce_min_sync(0xffffffffu, __float_as_uint(fb));
+                    if (lane == 0 && sp < BVH_STACK) {
+                        s_ref[warp][sp] = left_first ? right : left;
+                        s_bound[warp][sp] = __uint_as_float(fmin);
+                    }
+                    if (sp < BVH_STACK) ++sp;
+                    __syncwarp();
+                    cur = left_first ? left : right;
+                    continue;
+                }
+                if (ml != 0u) { cur = left; continue; }
+                if (mr != 0u) { cur = right; continue; }
+            }
+            bool found = false;
+            while (sp > 0) {
+                --sp;
+                const float pb = s_bound[warp][sp];
+                const int pr = s_ref[warp][sp];
+                if (__ballot_sync(0xffffffffu, active && !(pb * BVH_SHRINK > prune_d)) != 0u) {
+                    cur = pr; found = true; break;
+                }
+            }
+            __syncwarp();
+            if (!found) break;
+        }
+    }
+    if (active) keys[t] = best;
+    if (FUSED) {
+        // K3 + K4 for this thread's query (functions/general.py:299-306, :160-181)
+        double acc[MOM];
+#pragma unroll
+        for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
+        if (active && best != KEY_NONE) {
+            float wqx, wqy, wqz, w1x, w1y, w1z;
+            s1_matvec(st->mw_base, x, y, z, wqx, wqy, wqz);
+            s1_matvec(st->mw_base, wx, wy, wz, w1x, w1y, w1z);
+            const double dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+            if (dist < thresh) {
+                float bx, by, bz;
+                s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);
+                moments_add(acc, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2]);
+            }
+        }
+        block_reduce_moments<PKT_THREADS>(acc, partials);
+    }
+}
+
 }  // namespace icp
