@@ -356,6 +356,8 @@ def run_ours(args, rank, world, local_rank):
         "bound": "fp32",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "traffic": traffic,
+        "dram_gbs_from_traffic": (traffic / (nn_avg_ms * 1e-3) / 1e9) if (traffic and nn_avg_ms > 0) else None,
+        "dram_frac_of_hbm_peak": (traffic / (nn_avg_ms * 1e-3) / 1e9 / hbm_peak_of(peaks)) if (traffic and nn_avg_ms > 0) else None,
         "peak_source": "FFMA/FFMA2 micro-benchmark measured in this run (icp_measure_fp32_peak); "
                        "MEASURED_PEAKS.json has no fp32 CUDA-core figure",
         "algorithmic": "8 FLOP x M_eff x N_local pair evaluations per launch (SURVEY 8d)",
@@ -367,7 +369,7 @@ def run_ours(args, rank, world, local_rank):
         "issue_model": {"sm_cycles_per_pair_lane": cyc_per_pair,
                         "floor_cycles_per_pair": BRUTEFORCE_FLOOR.get(bruteforce_kernel_name(args.nn_variant, n_local).split("<")[0]),
                         "note": "floor = 2 cycles x (FFMA2 + FMNMX3 warp instructions per pair): direct 3.5, "
-                                "expansion filter 2.0, cylinder filter 1.5 instructions per pair"},
+                                "expansion filter 2.0, cylinder filter 1.5, slab filter 1.0 instructions per pair"},
         "why_not_hbm": "brute-force NN is fp32-issue bound: %.0f MB compulsory traffic per iteration vs "
                        "%.1e pair evaluations (SURVEY D4)" % ((12 * n_local + 52 * m) / 1e6, float(m) * n_local),
     }
@@ -424,14 +426,17 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-BRUTEFORCE_FLOOR = {"k_nn_bruteforce": 7.0, "k_nn_bruteforce_filter": 4.0, "k_nn_bruteforce_cyl": 3.0}
+BRUTEFORCE_FLOOR = {"k_nn_bruteforce": 7.0, "k_nn_bruteforce_filter": 4.0, "k_nn_bruteforce_cyl": 3.0,
+                    "k_nn_bruteforce_slab": 2.0}
 
 
 def bruteforce_kernel_name(variant, n_local):
     """The K2 kernel the library picks for the timed (seeded) passes (icp_b200.cu launch_nn)."""
     tiles = (n_local + 1023) // 1024
     if variant == 0:
-        return "k_nn_bruteforce_cyl<4,3,32>" if tiles >= 16 else "k_nn_bruteforce<4,4,1>"
+        return "k_nn_bruteforce_slab<4,3,64>" if tiles >= 16 else "k_nn_bruteforce<4,4,1>"
+    if 40 <= variant <= 43:
+        return "k_nn_bruteforce_slab"
     if 30 <= variant <= 36:
         return "k_nn_bruteforce_cyl"
     if 20 <= variant <= 29:

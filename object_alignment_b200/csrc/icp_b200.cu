@@ -31,6 +31,7 @@
 #include "icp_state.cuh"
 #include "nn_bruteforce.cuh"
 #include "nn_bruteforce_cyl.cuh"
+#include "nn_bruteforce_slab.cuh"
 #include "nn_bvh.cuh"
 #include "nn_surface.cuh"
 
@@ -732,6 +733,11 @@ struct icp_handle {
     CylTileHdr* d_cyl_hdrs = nullptr;
     int cyl_axes = 0;                      // a | b << 2 | c << 4
     int cyl_sorted = -1;                   // how the current tiles were built (-1: not built)
+    float* d_slab_ftiles = nullptr;        // [tile][a'|b'|w2|c'|w1][1024], vertices sorted along a inside a tile
+    float* d_slab_etiles = nullptr;        // [tile][x|y|z|original index][1024], same order
+    CylTileHdr* d_slab_hdrs = nullptr;
+    int slab_axes = 0;
+    bool slab_built = false;
     // spatial index (nn_mode == ICP_NN_BVH), built lazily from d_base4
     BvhNode* d_bvh_nodes = nullptr;
     float4* d_bvh_sorted = nullptr;
@@ -836,12 +842,16 @@ int ensure(icp_handle* h, T*& ptr, long long& cap, long long need)
 }
 
 // brute-force variants.  0 (default): query slots in Morton order; the unseeded first pass runs the
-// expansion-filter kernel (or the direct kernel on small shards), every later pass the cylinder
-// kernel over Morton-ordered, per-tile-centred base tiles, seeded with the previous winners.
+// expansion-filter kernel (or the direct kernel on small shards), every later pass the slab kernel
+// (1-fma plane bound, then the 2-fma cylinder bound, then the exact metric) over Morton-ordered,
+// per-tile-centred base tiles, seeded with the previous winners.
 // 1..6 direct metric, 20..24 expansion filter, 30..36 cylinder filter on every pass:
 // 30 = sorted base + sorted query slots, 31 = base in its own order, 32 = queries in their own
 // order, 33 = neither, 34..36 = 30 with other blockings (8 queries/thread, 32-vertex chunks, both).
+// 40..43 slab filter (1 fma per pair) in front of the cylinder filter: 40 = 4 queries/thread and 32-vertex
+// chunks, 41 = 8 queries/thread, 42 = 64-vertex chunks, 43 = both.
 bool cyl_variant(int v) { return v >= 30 && v <= 36; }
+bool slab_variant(int v) { return v >= 40 && v <= 43; }
 bool cyl_sorts_base(const icp_handle* h)
 {
     const int v = h->prm.nn_variant;
@@ -851,7 +861,7 @@ bool uses_slots(const icp_handle* h)
 {
     if (h->prm.nn_mode != ICP_NN_BRUTEFORCE) return true;
     const int v = h->prm.nn_variant;
-    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36);
+    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36) || slab_variant(v);
 }
 
 long long query_count(const icp_handle* h)
@@ -1069,12 +1079,99 @@ int launch_nn_cyl_t(icp_handle* h, long long n_q)
     return ICP_OK;
 }
 
+// Slab tiles: Morton order decides which 1024 vertices share a tile, then each tile is sorted along
+// the axis of largest extent (one more radix sort on (tile, coordinate) keys).  One-time per base.
+int build_slab(icp_handle* h)
+{
+    if (h->slab_built) return ICP_OK;
+    for (void* p : {(void*)h->d_slab_ftiles, (void*)h->d_slab_etiles, (void*)h->d_slab_hdrs}) if (p) cudaFree(p);
+    h->d_slab_ftiles = h->d_slab_etiles = nullptr; h->d_slab_hdrs = nullptr;
+    const long long n = h->n_local;
+    if (n > 0) {
+        unsigned long long *codes = nullptr, *codes_out = nullptr;
+        uint32_t *order = nullptr, *order_out = nullptr;
+        float *part = nullptr, *bbox = nullptr;
+        void* temp = nullptr;
+        size_t temp_bytes = 0;
+        const int pb = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
+        const unsigned gn = (unsigned)((n + 255) / 256);
+        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 24));
+        CUDA_TRY(h, cudaMalloc((void**)&bbox, 24));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_slab_ftiles, (size_t)h->n_tiles * SLAB_TILE_BYTES));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_slab_etiles, (size_t)h->n_tiles * CYL_TILE_BYTES));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_slab_hdrs, (size_t)h->n_tiles * sizeof(CylTileHdr)));
+        CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&order, (size_t)n * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&order_out, (size_t)n * 4));
+        k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
+        k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
+        k_morton_codes<<<gn, 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order);
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 64, h->stream));
+        CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
+        // a = largest extent (the slab axis), c = smallest (dropped by the cylinder bound), b = the third
+        float hb[6];
+        CUDA_TRY(h, cudaMemcpyAsync(hb, bbox, 24, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ext[3];
+        for (int k = 0; k < 3; ++k) { ext[k] = hb[3 + k] - hb[k]; if (!(ext[k] >= 0.0f)) ext[k] = 0.0f; }
+        int a = 0, c = 2;
+        for (int k = 1; k < 3; ++k) if (ext[k] > ext[a]) a = k;
+        for (int k = 1; k >= 0; --k) if (ext[k] < ext[c]) c = k;
+        if (c == a) c = (a + 2) % 3;
+        const int b = 3 - a - c;
+        h->slab_axes = a | (b << 2) | (c << 4);
+        k_slab_keys<<<gn, 256, 0, h->stream>>>(h->d_base4, order_out, n, a, codes);
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order_out, order, (int)n, 0, 64, h->stream));
+        k_build_slab_tiles<<<(unsigned)h->n_tiles, 256, 0, h->stream>>>(h->d_base4, order, n, a, b, c, h->d_slab_ftiles,
+                                                                       h->d_slab_etiles, h->d_slab_hdrs);
+        h->launches += 7;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (void* p : {(void*)codes, (void*)codes_out, (void*)order, (void*)order_out, (void*)part, (void*)bbox, temp}) if (p) cudaFree(p);
+    }
+    h->slab_built = true;
+    return ICP_OK;
+}
+
+template <int R, int STAGES, int CH>
+int launch_nn_slab_t(icp_handle* h, long long n_q)
+{
+    auto kern = k_nn_bruteforce_slab<R, STAGES, CH>;
+    const size_t smem = (size_t)STAGES * SLAB_TILE_BYTES + STAGES * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)h->sm_count * occ;
+    long long want_y = (8 * slots + qb - 1) / qb;
+    long long max_y = std::max<long long>(1, h->n_tiles / 8);
+    long long gy = std::max<long long>(1, std::min(want_y, max_y));
+    int tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy);
+    gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    if (gy > 65535) { gy = 65535; tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy); gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta; }
+    dim3 grid((unsigned)qb, (unsigned)gy);
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->slab_axes, h->n_tiles,
+                                                tiles_per_cta, qx, qy, qz, n_q, h->d_keys, (uint32_t)h->base_off,
+                                                h->bf_warm_active ? 1 : 0, &h->d_state->converged);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
 int launch_nn(icp_handle* h, long long n_q)
 {
     if (n_q <= 0 || h->n_tiles <= 0) return ICP_OK;
     int variant = h->prm.nn_variant;
     if (variant == 0) {
-        if (h->bf_warm_active && h->n_tiles >= 16) variant = 35;       // seeded: cylinder kernel
+        if (h->bf_warm_active && h->n_tiles >= 16) variant = 42;       // seeded: slab + cylinder filter kernel
         else variant = h->n_tiles >= 256 ? 20 : 2;                     // cold: filter / direct kernel
     }
     if (variant >= 20 && variant <= 29) {
@@ -1085,8 +1182,16 @@ int launch_nn(icp_handle* h, long long n_q)
         int rc = build_cyl(h);
         if (rc) return rc;
     }
+    if (slab_variant(variant)) {
+        int rc = build_slab(h);
+        if (rc) return rc;
+    }
     ProfScope ps(h, 0);
     switch (variant) {
+        case 40: return launch_nn_slab_t<4, 3, 32>(h, n_q);
+        case 41: return launch_nn_slab_t<8, 3, 32>(h, n_q);
+        case 42: return launch_nn_slab_t<4, 3, 64>(h, n_q);
+        case 43: return launch_nn_slab_t<8, 3, 64>(h, n_q);
         case 30: case 31: case 32: case 33: return launch_nn_cyl_t<4, 3, 16>(h, n_q);
         case 34: return launch_nn_cyl_t<8, 3, 16>(h, n_q);
         case 35: return launch_nn_cyl_t<4, 3, 32>(h, n_q);
@@ -1606,7 +1711,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1643,6 +1748,7 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
     h->bvh_built = false;
     h->filter_built = false;
     h->cyl_sorted = -1;
+    h->slab_built = false;
     h->warm_valid = false;
     h->bf_warm_valid = false;
     if (n_local > 0) {

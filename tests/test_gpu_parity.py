@@ -94,7 +94,7 @@ def test_nn_vlist_stride_and_matrices():
         assert np.array_equal(d2.view(np.uint32), res["d2"].view(np.uint32))
 
 
-@pytest.mark.parametrize("variant", [20, 21, 30, 33, 35, 36])
+@pytest.mark.parametrize("variant", [20, 21, 30, 33, 35, 36, 40, 43])
 @pytest.mark.parametrize("case", ["surface", "far_outliers", "duplicates", "collinear", "volume", "lattice",
                                   "far_from_origin", "sorted_base"])
 def test_filter_kernel_matches_oracle(case, variant):
@@ -123,7 +123,7 @@ def test_filter_kernel_matches_oracle(case, variant):
 def test_filter_kernel_equals_direct_kernel_at_1m():
     cfg = meshgen.config_cloud(1_000_000, 1_000_000, 200, 201)
     res = {}
-    for variant in (2, 20, 35, 0):
+    for variant in (2, 20, 35, 40, 0):
         with IcpEngine(nn_variant=variant) as e:
             e.set_base(cfg["base"])
             e.set_moving(cfg["moving"])
@@ -131,7 +131,7 @@ def test_filter_kernel_equals_direct_kernel_at_1m():
             res[variant] = e.nn()
             if variant == 0:
                 res["seeded"] = e.nn()           # second pass: seeded cylinder kernel
-    for other in (20, 35, 0, "seeded"):
+    for other in (20, 35, 40, 0, "seeded"):
         assert np.array_equal(res[2][0], res[other][0]) and np.array_equal(res[2][1], res[other][1])
 
 
@@ -418,7 +418,7 @@ def test_bvh_warm_start_stays_exact_over_iterations():
             np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(res["A"], res["B"]), atol=1e-10)
 
 
-@pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36])
+@pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36, 40, 41, 42])
 def test_bruteforce_seeded_passes_stay_exact(variant):
     """From the second pass on the brute-force filter kernel starts its running minimum from the
     previous winner re-evaluated under the new pose.  Every pass must still return the oracle's

@@ -20,10 +20,10 @@ echo "bvh/surface bench rc=$?"
 
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
     --log-file $O/launches_c3_default.csv $BENCH_NCU > $O/ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_nn_bruteforce_cyl -s 3 -c 1 \
-    -f -o $O/ncu_cyl $BENCH_NCU > $O/ncu_cyl.log 2>&1
-ncu -i $O/ncu_cyl.ncu-rep --page details --csv > $O/ncu_details_cyl.csv 2>/dev/null
-ncu -i $O/ncu_cyl.ncu-rep --page raw --csv > $O/ncu_raw_cyl.csv 2>/dev/null
+ncu --set full --clock-control none --import-source on -k regex:k_nn_bruteforce_slab -s 3 -c 1 \
+    -f -o $O/ncu_slab $BENCH_NCU > $O/ncu_slab.log 2>&1
+ncu -i $O/ncu_slab.ncu-rep --page details --csv > $O/ncu_details_slab.csv 2>/dev/null
+ncu -i $O/ncu_slab.ncu-rep --page raw --csv > $O/ncu_raw_slab.csv 2>/dev/null
 ncu --set full --clock-control none --import-source on -k regex:k_nn_bvh -s 4 -c 1 \
     -f -o $O/ncu_bvh $BENCH_NCU --nn-mode bvh > $O/ncu_bvh.log 2>&1
 ncu -i $O/ncu_bvh.ncu-rep --page details --csv > $O/ncu_details_bvh.csv 2>/dev/null
