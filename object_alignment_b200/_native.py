@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicp_b200.so")
+# ICP_B200_LIB points at another build of the same library (A/B experiments); there is still no fallback
+LIB_PATH = os.environ.get("ICP_B200_LIB") or os.path.join(_HERE, "libicp_b200.so")
 
 ICP_OK = 0
 ICP_ERR_BAD_ARG = 1

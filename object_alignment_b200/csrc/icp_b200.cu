@@ -406,17 +406,20 @@ k_pairs_moments(const double* __restrict__ v0, const double* __restrict__ v1, lo
     }
 }
 
-// fixed-order sum of the per-CTA partials -> moments[MOM]   (one CTA of MOM warps)
+// fixed-order sum of the per-CTA partials -> moments[MOM]   (CTAs of MOM warps; CTA b sums the slice
+// [b * per_cta, (b + 1) * per_cta) into out[b][MOM]; the last stage is one CTA over everything left)
 __global__ void k_reduce_moments(const DevState* __restrict__ st, const double* __restrict__ partials,
-                                 int n_partials, double* __restrict__ moments)
+                                 int n_partials, double* __restrict__ moments, int per_cta = 0x7fffffff)
 {
     if (st != nullptr && st->converged) return;
     const int lane = threadIdx.x & 31, comp = threadIdx.x >> 5;
     if (comp >= MOM) return;
+    const long long lo = (long long)blockIdx.x * per_cta;
+    const long long hi = lo + per_cta < n_partials ? lo + per_cta : n_partials;
     double v = 0.0;
-    for (int i = lane; i < n_partials; i += 32) v += partials[(size_t)i * MOM + comp];
+    for (long long i = lo + lane; i < hi; i += 32) v += partials[(size_t)i * MOM + comp];
     v = warp_sum(v);
-    if (lane == 0) moments[comp] = v;
+    if (lane == 0) moments[(size_t)blockIdx.x * MOM + comp] = v;
 }
 
 // Kabsch/Umeyama step from the moments (general.py:160-217 for shear=False, usesvd=True)
@@ -737,7 +740,7 @@ struct icp_handle {
     float* d_slab_etiles = nullptr;        // [tile][x|y|z|original index][1024], same order
     CylTileHdr* d_slab_hdrs = nullptr;
     int slab_axes = 0;
-    bool slab_built = false;
+    int slab_order = -1;                   // -1 not built, 0 sorted along a inside a tile, 1 Morton order inside a tile
     // spatial index (nn_mode == ICP_NN_BVH), built lazily from d_base4
     BvhNode* d_bvh_nodes = nullptr;
     float4* d_bvh_sorted = nullptr;
@@ -772,6 +775,7 @@ struct icp_handle {
     long long q_capacity = 0;
     // reductions
     double* d_partials = nullptr;
+    double* d_partials2 = nullptr;         // second reduction stage (64 slices)
     int partials_capacity = 0;
     double* d_moments = nullptr;
     unsigned int* d_hist = nullptr;
@@ -851,7 +855,7 @@ int ensure(icp_handle* h, T*& ptr, long long& cap, long long need)
 // 40..43 slab filter (1 fma per pair) in front of the cylinder filter: 40 = 4 queries/thread and 32-vertex
 // chunks, 41 = 8 queries/thread, 42 = 64-vertex chunks, 43 = both.
 bool cyl_variant(int v) { return v >= 30 && v <= 36; }
-bool slab_variant(int v) { return v >= 40 && v <= 43; }
+bool slab_variant(int v) { return v >= 40 && v <= 45; }   // 44, 45 = 40, 42 with Morton order inside a tile
 bool cyl_sorts_base(const icp_handle* h)
 {
     const int v = h->prm.nn_variant;
@@ -1083,7 +1087,8 @@ int launch_nn_cyl_t(icp_handle* h, long long n_q)
 // the axis of largest extent (one more radix sort on (tile, coordinate) keys).  One-time per base.
 int build_slab(icp_handle* h)
 {
-    if (h->slab_built) return ICP_OK;
+    const int want_order = (h->prm.nn_variant == 44 || h->prm.nn_variant == 45) ? 1 : 0;
+    if (h->slab_order == want_order) return ICP_OK;
     for (void* p : {(void*)h->d_slab_ftiles, (void*)h->d_slab_etiles, (void*)h->d_slab_hdrs}) if (p) cudaFree(p);
     h->d_slab_ftiles = h->d_slab_etiles = nullptr; h->d_slab_hdrs = nullptr;
     const long long n = h->n_local;
@@ -1122,16 +1127,18 @@ int build_slab(icp_handle* h)
         if (c == a) c = (a + 2) % 3;
         const int b = 3 - a - c;
         h->slab_axes = a | (b << 2) | (c << 4);
-        k_slab_keys<<<gn, 256, 0, h->stream>>>(h->d_base4, order_out, n, a, codes);
-        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order_out, order, (int)n, 0, 64, h->stream));
-        k_build_slab_tiles<<<(unsigned)h->n_tiles, 256, 0, h->stream>>>(h->d_base4, order, n, a, b, c, h->d_slab_ftiles,
-                                                                       h->d_slab_etiles, h->d_slab_hdrs);
+        if (want_order == 0) {
+            k_slab_keys<<<gn, 256, 0, h->stream>>>(h->d_base4, order_out, n, a, codes);
+            CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order_out, order, (int)n, 0, 64, h->stream));
+        }
+        k_build_slab_tiles<<<(unsigned)h->n_tiles, 256, 0, h->stream>>>(h->d_base4, want_order == 0 ? order : order_out, n, a, b, c,
+                                                                       h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs);
         h->launches += 7;
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         for (void* p : {(void*)codes, (void*)codes_out, (void*)order, (void*)order_out, (void*)part, (void*)bbox, temp}) if (p) cudaFree(p);
     }
-    h->slab_built = true;
+    h->slab_order = want_order;
     return ICP_OK;
 }
 
@@ -1139,7 +1146,7 @@ template <int R, int STAGES, int CH>
 int launch_nn_slab_t(icp_handle* h, long long n_q)
 {
     auto kern = k_nn_bruteforce_slab<R, STAGES, CH>;
-    const size_t smem = (size_t)STAGES * SLAB_TILE_BYTES + STAGES * sizeof(uint64_t);
+    const size_t smem = (size_t)STAGES * SLAB_TILE_BYTES + 2 * STAGES * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
         CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1192,6 +1199,8 @@ int launch_nn(icp_handle* h, long long n_q)
         case 41: return launch_nn_slab_t<8, 3, 32>(h, n_q);
         case 42: return launch_nn_slab_t<4, 3, 64>(h, n_q);
         case 43: return launch_nn_slab_t<8, 3, 64>(h, n_q);
+        case 44: return launch_nn_slab_t<4, 3, 32>(h, n_q);
+        case 45: return launch_nn_slab_t<4, 3, 64>(h, n_q);
         case 30: case 31: case 32: case 33: return launch_nn_cyl_t<4, 3, 16>(h, n_q);
         case 34: return launch_nn_cyl_t<8, 3, 16>(h, n_q);
         case 35: return launch_nn_cyl_t<4, 3, 32>(h, n_q);
@@ -1271,6 +1280,7 @@ int launch_nn_bvh(icp_handle* h, long long n_q)
     ProfScope ps(h, 0);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     const unsigned g128 = (unsigned)((n_q + 127) / 128);
+    const unsigned gpk = (unsigned)((n_q + PKT_THREADS - 1) / PKT_THREADS);
     const int v = h->prm.nn_variant;
     if (v == 99) {          // debug: per-thread walk with visit counters (icp_debug_counters)
         k_nn_bvh<true><<<g128, 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, n_q,
@@ -1279,11 +1289,11 @@ int launch_nn_bvh(icp_handle* h, long long n_q)
         k_nn_bvh<false><<<g128, 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, n_q,
                                                      h->d_keys, (uint32_t)h->base_off, &h->d_state->converged);
     } else if (v == 98) {   // debug: warp-packet walk with visit counters
-        k_nn_bvh_packet<false, true><<<g128, PKT_THREADS, 0, h->stream>>>(
+        k_nn_bvh_packet<false, true><<<gpk, PKT_THREADS, 0, h->stream>>>(
             h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0,
             n_q, h->d_keys, (uint32_t)h->base_off, nullptr);
     } else {                // default: warp-packet walk
-        k_nn_bvh_packet<false, false><<<g128, PKT_THREADS, 0, h->stream>>>(
+        k_nn_bvh_packet<false, false><<<gpk, PKT_THREADS, 0, h->stream>>>(
             h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0,
             n_q, h->d_keys, (uint32_t)h->base_off, nullptr);
     }
@@ -1468,9 +1478,9 @@ int launch_nn_surface(icp_handle* h, long long n_q)
     if (n_q <= 0 || h->n_local <= 0) return ICP_OK;
     ProfScope ps(h, 0);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
-    const unsigned g = (unsigned)((n_q + 127) / 128);
+    const unsigned g = (unsigned)((n_q + PKT_THREADS - 1) / PKT_THREADS);
     if (h->prm.nn_variant == 10) {       // per-thread walk (kept for A/B runs and as a cross-check)
-        k_nn_surface<<<g, 128, 0, h->stream>>>(h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz,
+        k_nn_surface<<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz,
                                                n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent,
                                                &h->d_state->converged);
     } else {                             // default: warp-packet walk
@@ -1480,6 +1490,24 @@ int launch_nn_surface(icp_handle* h, long long n_q)
     }
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+// sum `g` per-CTA partial vectors into h->d_moments: one CTA, or 64 slice CTAs + one when there are many
+int launch_reduce(icp_handle* h, const DevState* st, int g)
+{
+    constexpr int SLICES = 64;
+    if (g <= 2048) {
+        k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(st, h->d_partials, g, h->d_moments);
+        h->launches += 1;
+        return ICP_OK;
+    }
+    if (!h->d_partials2) CUDA_TRY(h, cudaMalloc((void**)&h->d_partials2, (size_t)SLICES * MOM * sizeof(double)));
+    const int per = (g + SLICES - 1) / SLICES;
+    const int nb = (g + per - 1) / per;
+    k_reduce_moments<<<nb, MOM * 32, 0, h->stream>>>(st, h->d_partials, g, h->d_partials2, per);
+    k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(st, h->d_partials2, nb, h->d_moments);
+    h->launches += 2;
     return ICP_OK;
 }
 
@@ -1533,8 +1561,8 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     h->bf_warm_valid = false;
     {
         ProfScope ps(h, 2);
-        k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
-        h->launches += 1;
+        rc = launch_reduce(h, h->d_state, g);
+        if (rc) return rc;
     }
     if (h->prm.world_size > 1) {      // queries sharded: the only exchange is the 20-double moment sum
         if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
@@ -1711,7 +1739,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1748,7 +1776,7 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
     h->bvh_built = false;
     h->filter_built = false;
     h->cyl_sorted = -1;
-    h->slab_built = false;
+    h->slab_order = -1;
     h->warm_valid = false;
     h->bf_warm_valid = false;
     if (n_local > 0) {

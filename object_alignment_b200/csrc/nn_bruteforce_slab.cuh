@@ -34,9 +34,10 @@
 
 namespace icp {
 
-constexpr int SLAB_PLANES = 5;                               // a' | b' | w2 | c' | w1
+constexpr int SLAB_PLANES = 6;                               // a' | b' | w2 | c' | a'^2 | b'^2
 constexpr int SLAB_TILE_FLOATS = NN_TILE * SLAB_PLANES;
-constexpr int SLAB_TILE_BYTES = SLAB_TILE_FLOATS * 4;        // 20 KB per TMA bulk copy
+constexpr int SLAB_TILE_BYTES = SLAB_TILE_FLOATS * 4;        // 24 KB per TMA bulk copy
+constexpr int SLAB_WARPS = NN_THREADS / 32;
 
 __device__ __forceinline__ uint32_t orderable_bits(float f)
 {
@@ -111,17 +112,18 @@ k_build_slab_tiles(const float4* __restrict__ base4, const uint32_t* __restrict_
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int i = k * 256 + tid;
-        float pa = 0.0f, pb = 0.0f, pc = 0.0f, w2 = inf, w1 = inf;
+        float pa = 0.0f, pb = 0.0f, pc = 0.0f, w2 = inf, wa = inf, wb = inf;
         if (fin[k]) {
             pa = __fsub_rn(axis_of(x[k], y[k], z[k], axis_a), ca);
             pb = __fsub_rn(axis_of(x[k], y[k], z[k], axis_b), cb);
             pc = __fsub_rn(axis_of(x[k], y[k], z[k], axis_c), cc);
-            w1 = __fmul_rn(pa, pa);
-            w2 = __fmaf_rn(pb, pb, w1);
+            wa = __fmul_rn(pa, pa);
+            wb = __fmul_rn(pb, pb);
+            w2 = __fmaf_rn(pb, pb, wa);
             b2 = fmaxf(b2, __fmaf_rn(pc, pc, w2));
         }
         ft[i] = pa; ft[NN_TILE + i] = pb; ft[2 * NN_TILE + i] = w2; ft[3 * NN_TILE + i] = pc;
-        ft[4 * NN_TILE + i] = w1;
+        ft[4 * NN_TILE + i] = wa; ft[5 * NN_TILE + i] = wb;
         et[i] = x[k]; et[NN_TILE + i] = y[k]; et[2 * NN_TILE + i] = z[k];
         et[3 * NN_TILE + i] = __uint_as_float(oi[k]);
     }
@@ -139,16 +141,18 @@ k_build_slab_tiles(const float4* __restrict__ base4, const uint32_t* __restrict_
     }
 }
 
-// per (query, tile): the multiplier and the chunk threshold in F1 space
+// per (query, tile): the multiplier and the chunk threshold in F1 space; `use_b` (warp-uniform) picks
+// the slab axis for this tile -- any axis gives a valid bound, the one along which the warp's queries
+// are farther from the tile centre gives the stronger one
 __device__ __forceinline__ void slab_setup(float qa, float qb, float qc, const CylTileHdr& h, float best,
-                                           float& ax, float& thr1)
+                                           bool use_b, float& ax, float& thr1)
 {
     const float pa = __fsub_rn(qa, h.ca), pb = __fsub_rn(qb, h.cb), pc = __fsub_rn(qc, h.cc);
-    const float nq1 = __fmul_rn(pa, pa);
-    const float nq3 = __fmaf_rn(pc, pc, __fmaf_rn(pb, pb, nq1));
+    const float na = __fmul_rn(pa, pa), nb = __fmul_rn(pb, pb);
+    const float nq3 = __fmaf_rn(pc, pc, __fadd_rn(na, nb));
     const float delta = 4.0e-6f * (nq3 + h.b2);
-    ax = -2.0f * pa;
-    thr1 = (best + delta) - nq1;
+    ax = -2.0f * (use_b ? pb : pa);
+    thr1 = (best + delta) - (use_b ? nb : na);
 }
 
 // Second filter level (out of line): minimum of the cylinder bound F over one chunk, packed.
@@ -171,8 +175,18 @@ __device__ __noinline__ float cyl_chunk_min(const float* fx, float ax, float ay,
     return m;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // grid.x = query blocks of NN_THREADS * R slots, grid.y = base ranges of tiles_per_cta tiles.
-// Dynamic shared memory: STAGES * SLAB_TILE_BYTES + STAGES * 8 (mbarriers).
+// Dynamic shared memory: STAGES * SLAB_TILE_BYTES + 2 * STAGES * 8 (full / empty mbarriers).
+//
+// Tile ring without a CTA-wide barrier: a warp that has finished a tile arrives on the slot's `empty`
+// mbarrier; thread 0 refills a slot one tile LATE (at the end of tile it it refills the slot of tile
+// it - 1), by which time every warp has normally left that slot, so a warp delayed by slow-path work
+// no longer stalls the other seven (ncu: 10 % of the samples sat on the per-tile __syncthreads).
 template <int R, int STAGES, int CH>
 __global__ void __launch_bounds__(NN_THREADS)
 k_nn_bruteforce_slab(const float* __restrict__ ftiles, const float* __restrict__ etiles,
@@ -186,15 +200,16 @@ k_nn_bruteforce_slab(const float* __restrict__ ftiles, const float* __restrict__
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * SLAB_TILE_BYTES);
+    uint64_t* empty = full + STAGES;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int t0 = blockIdx.y * tiles_per_cta;
     const int t1 = min(n_tiles, t0 + tiles_per_cta);
     const int my_tiles = t1 - t0;
     if (my_tiles <= 0) return;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SLAB_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -228,13 +243,15 @@ k_nn_bruteforce_slab(const float* __restrict__ ftiles, const float* __restrict__
     for (int it = 0; it < my_tiles; ++it) {
         const int slot = it % STAGES;
         const CylTileHdr hdr = hdrs[t0 + it];
+        // slab axis of this (warp, tile): the one along which most lanes are farther from the tile centre
+        const bool use_b = __popc(__ballot_sync(0xffffffffu, fabsf(qb[0] - hdr.cb) > fabsf(qa[0] - hdr.ca))) > 16;
         float ax[R], thr[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) slab_setup(qa[r], qb[r], qc[r], hdr, best[r], ax[r], thr[r]);
+        for (int r = 0; r < R; ++r) slab_setup(qa[r], qb[r], qc[r], hdr, best[r], use_b, ax[r], thr[r]);
         mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
         const float* tile = tiles + (size_t)slot * SLAB_TILE_FLOATS;
-        const float4* sa = reinterpret_cast<const float4*>(tile);
-        const float4* s1 = reinterpret_cast<const float4*>(tile + 4 * NN_TILE);
+        const float4* sa = reinterpret_cast<const float4*>(tile + (use_b ? NN_TILE : 0));
+        const float4* s1 = reinterpret_cast<const float4*>(tile + (use_b ? 5 * NN_TILE : 4 * NN_TILE));
 #pragma unroll 1
         for (int c = 0; c < NN_TILE / CH; ++c) {
             float cm[R];
@@ -269,15 +286,18 @@ k_nn_bruteforce_slab(const float* __restrict__ ftiles, const float* __restrict__
                     bkey[r] = cyl_recheck(fx, ex, hdr.ca, hdr.cb, hdr.cc, hdr.b2, qa[r], qb[r], qc[r], axes, CH,
                                           index_offset, bkey[r]);
                     best[r] = key_d2(bkey[r]);
-                    slab_setup(qa[r], qb[r], qc[r], hdr, best[r], ax[r], thr[r]);
+                    slab_setup(qa[r], qb[r], qc[r], hdr, best[r], use_b, ax[r], thr[r]);
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0 && it + STAGES < my_tiles) {
-            mbar_expect_tx(&full[slot], SLAB_TILE_BYTES);
-            tma_load_1d(tiles + (size_t)slot * SLAB_TILE_FLOATS,
-                        ftiles + (size_t)(t0 + it + STAGES) * SLAB_TILE_FLOATS, SLAB_TILE_BYTES, &full[slot]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);                   // this warp is done with the slot
+        if (tid == 0 && it >= 1 && it - 1 + STAGES < my_tiles) {    // late refill of the previous slot
+            const int j = it - 1, js = j % STAGES;
+            mbar_wait(&empty[js], (uint32_t)((j / STAGES) & 1));
+            mbar_expect_tx(&full[js], SLAB_TILE_BYTES);
+            tma_load_1d(tiles + (size_t)js * SLAB_TILE_FLOATS, ftiles + (size_t)(t0 + j + STAGES) * SLAB_TILE_FLOATS,
+                        SLAB_TILE_BYTES, &full[js]);
         }
     }
 #pragma unroll

@@ -319,7 +319,14 @@ k_nn_bvh(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, i
 // the previous winner) in its prologue and K3+K4 (world distance, thresh, target, fp64 moment
 // partials) in its epilogue, so an ICP iteration is this kernel + one single-CTA solve.
 // ---------------------------------------------------------------------------------------------
-constexpr int PKT_THREADS = 128;
+#ifndef ICP_PKT_THREADS
+#define ICP_PKT_THREADS 128
+#endif
+// 4 warps per CTA.  A CTA's registers are only released when its slowest warp has finished its walk
+// (ncu: 20 % of the surface kernel's samples wait in the epilogue barrier); a one-warp build
+// (-DICP_PKT_THREADS=32) was 10 % faster on the surface walk but faulted in the vertex walk
+// (compute-sanitizer: out-of-range node reference) and is NOT supported until that is understood.
+constexpr int PKT_THREADS = ICP_PKT_THREADS;
 
 template <bool FUSED, bool COUNT>
 __global__ void __launch_bounds__(PKT_THREADS)
