@@ -1478,13 +1478,17 @@ int launch_nn_surface(icp_handle* h, long long n_q)
     if (n_q <= 0 || h->n_local <= 0) return ICP_OK;
     ProfScope ps(h, 0);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
-    const unsigned g = (unsigned)((n_q + PKT_THREADS - 1) / PKT_THREADS);
+    const unsigned g = (unsigned)((n_q + SURF_THREADS - 1) / SURF_THREADS);
     if (h->prm.nn_variant == 10) {       // per-thread walk (kept for A/B runs and as a cross-check)
         k_nn_surface<<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz,
                                                n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent,
                                                &h->d_state->converged);
-    } else {                             // default: warp-packet walk
-        k_nn_surface_packet<false><<<g, PKT_THREADS, 0, h->stream>>>(
+    } else if (h->prm.nn_variant == 11 || h->n_local >= (1ll << 27)) {   // warp-packet walk, eager triangle tests
+        k_nn_surface_packet<false><<<g, SURF_THREADS, 0, h->stream>>>(
+            h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0,
+            n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent, nullptr);
+    } else {                             // default: warp-packet walk, deferred (queued) triangle tests
+        k_nn_surface_defer<false><<<g, SURF_THREADS, 0, h->stream>>>(
             h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0,
             n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent, nullptr);
     }
@@ -1535,7 +1539,8 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
         rc = build_bvh(h);
         if (rc) return rc;
     }
-    const int g = (int)std::max<long long>(1, (n_q + PKT_THREADS - 1) / PKT_THREADS);
+    const int cta = h->surface ? SURF_THREADS : PKT_THREADS;
+    const int g = (int)std::max<long long>(1, (n_q + cta - 1) / cta);
     rc = ensure_partials(h, g);
     if (rc) return rc;
     {
@@ -1545,8 +1550,13 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     }
     {
         ProfScope ps(h, 0);
-        if (h->surface)
-            k_nn_surface_packet<true><<<g, PKT_THREADS, 0, h->stream>>>(
+        if (h->surface && (h->prm.nn_variant == 11 || h->n_local >= (1ll << 27)))
+            k_nn_surface_packet<true><<<g, SURF_THREADS, 0, h->stream>>>(
+                h->d_tri_nodes, h->d_tri_sorted, h->n_local > 0 ? h->tri_runs : 0, nullptr, nullptr, nullptr, h->d_state,
+                h->d_mov_slots, h->d_tris4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
+                h->d_keys, (uint32_t)h->base_off, h->tri_extent, h->d_partials);
+        else if (h->surface)
+            k_nn_surface_defer<true><<<g, SURF_THREADS, 0, h->stream>>>(
                 h->d_tri_nodes, h->d_tri_sorted, h->n_local > 0 ? h->tri_runs : 0, nullptr, nullptr, nullptr, h->d_state,
                 h->d_mov_slots, h->d_tris4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
                 h->d_keys, (uint32_t)h->base_off, h->tri_extent, h->d_partials);
@@ -1585,7 +1595,7 @@ int enqueue_iteration(icp_handle* h, long long n_q)
     if ((h->prm.nn_mode == ICP_NN_BVH || h->prm.nn_mode == ICP_NN_SURFACE) &&
         (h->prm.world_size == 1 || h->prm.shard_mode == ICP_SHARD_QUERIES) &&
         !(h->prm.reject_fraction > 0) &&
-        h->prm.nn_variant != 10 && h->prm.nn_variant != 11 && h->prm.nn_variant != 99 && h->prm.nn_variant != 98)
+        h->prm.nn_variant != 10 && (h->prm.nn_variant != 11 || h->surface) && h->prm.nn_variant != 99 && h->prm.nn_variant != 98)
         return enqueue_iteration_fused(h, n_q);
     int rc = enqueue_nn(h, n_q);
     if (rc) return rc;

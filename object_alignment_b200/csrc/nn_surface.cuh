@@ -22,6 +22,19 @@ namespace icp {
 
 constexpr int TRI_LEAF = 4;
 
+// One warp per CTA for the surface walks: a CTA's registers are released only when its slowest warp
+// has finished, and the surface walk's tail is long (ncu: 20 % of the samples waited in the epilogue
+// barrier with 4 warps per CTA).  The kernels are COMPILED for up to 64 threads: with
+// __launch_bounds__(32) ptxas drops the warp syncs around the shared stack (it treats the CTA as one
+// converged warp), the votes then see a diverged subset and the walk follows garbage references
+// (caught by compute-sanitizer in the vertex walk).
+#ifndef ICP_SURF_THREADS
+#define ICP_SURF_THREADS 32
+#endif
+constexpr int SURF_THREADS = ICP_SURF_THREADS;
+constexpr int SURF_BOUNDS = SURF_THREADS < 64 ? 64 : SURF_THREADS;
+constexpr int SURF_WARPS = (SURF_THREADS + 31) / 32;
+
 __device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz)
 {
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
@@ -237,7 +250,7 @@ k_nn_surface(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorte
 // fp64 moment partials), so an ICP iteration is this kernel + one single-CTA solve.
 // ---------------------------------------------------------------------------------------------
 template <bool FUSED>
-__global__ void __launch_bounds__(PKT_THREADS)
+__global__ void __launch_bounds__(SURF_BOUNDS)
 k_nn_surface_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
                     const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
                     const DevState* __restrict__ st, const float4* __restrict__ mov_slots,
@@ -246,8 +259,8 @@ k_nn_surface_packet(const BvhNode* __restrict__ nodes, const float4* __restrict_
                     uint32_t index_offset, float coord_extent, double* __restrict__ partials)
 {
     if (st->converged) return;
-    __shared__ int s_ref[PKT_THREADS / 32][BVH_STACK];
-    __shared__ float s_bound[PKT_THREADS / 32][BVH_STACK];
+    __shared__ int s_ref[SURF_WARPS][BVH_STACK];
+    __shared__ float s_bound[SURF_WARPS][BVH_STACK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = t < n_queries;
@@ -370,7 +383,193 @@ k_nn_surface_packet(const BvhNode* __restrict__ nodes, const float4* __restrict_
                 moments_add(acc, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2]);
             }
         }
-        block_reduce_moments<PKT_THREADS>(acc, partials);
+        block_reduce_moments<SURF_THREADS>(acc, partials);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-packet walk with DEFERRED triangle tests (default).  At equal base and query density the 32
+// queries of a warp share few leaves, so in k_nn_surface_packet every lane pays an S9 test
+// (~120 instructions) for every triangle ANY lane needs: ncu put 65 % of the instructions there.
+// Here a leaf visit only runs a cheap per-lane box test per triangle and appends the surviving
+// (lane, triangle) pairs to a per-warp queue; whenever 32 pairs are queued the warp evaluates them
+// in ONE pass, one pair per lane (the owner's query comes by shuffle), and merges the keys into the
+// owners' bests with shared-memory atomicMin.  Deferring only delays the tightening of a bound, so
+// the walk visits a superset of what the eager walk visits and the winner is the same key.
+// ---------------------------------------------------------------------------------------------
+constexpr int SURF_QCAP = 32 + 32 * TRI_LEAF;     // queued pairs before a flush + one leaf's worth
+
+template <bool FUSED>
+__global__ void __launch_bounds__(SURF_BOUNDS)
+k_nn_surface_defer(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
+                   const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
+                   const DevState* __restrict__ st, const float4* __restrict__ mov_slots,
+                   const float4* __restrict__ tris4, long long base_off, long long n_local, double thresh,
+                   int warm, long long n_queries, unsigned long long* __restrict__ keys,
+                   uint32_t index_offset, float coord_extent, double* __restrict__ partials)
+{
+    if (st->converged) return;
+    __shared__ int s_ref[SURF_WARPS][BVH_STACK];
+    __shared__ float s_bound[SURF_WARPS][BVH_STACK];
+    __shared__ uint32_t s_queue[SURF_WARPS][SURF_QCAP];
+    __shared__ unsigned long long s_best[SURF_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < n_queries;
+    const float inf = __int_as_float(0x7f800000);
+
+    float x = 0.f, y = 0.f, z = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    unsigned long long best = KEY_NONE;
+    if (active) {
+        if (FUSED) {
+            const float4 a = mov_slots[t];
+            ax = a.x; ay = a.y; az = a.z;
+            float tx, ty, tz;
+            s1_matvec(st->mw_align, ax, ay, az, tx, ty, tz);
+            s1_matvec(st->imx2, tx, ty, tz, x, y, z);
+            if (warm) {
+                const unsigned long long old = keys[t];
+                const long long j = (long long)(uint32_t)(old & 0xFFFFFFFFull) - base_off;
+                if (old != KEY_NONE && j >= 0 && j < n_local) {
+                    const float4 a0 = tris4[3 * j], b0 = tris4[3 * j + 1], c0 = tris4[3 * j + 2];
+                    float rx, ry, rz;
+                    closest_on_tri(x, y, z, a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, c0.x, c0.y, c0.z, rx, ry, rz);
+                    const float d = s10_d2(x, y, z, rx, ry, rz);
+                    if (d < inf) best = ((unsigned long long)__float_as_uint(d) << 32) | (old & 0xFFFFFFFFull);
+                }
+            }
+        } else {
+            x = qx[t]; y = qy[t]; z = qz[t];
+            best = keys[t];
+        }
+    }
+    const float eta = 3.9e-6f * fmaxf(fmaxf(fabsf(x), fabsf(y)), fmaxf(fabsf(z), coord_extent));
+    float best_d = (best == KEY_NONE) ? inf : __uint_as_float((uint32_t)(best >> 32));
+    float prune_d = best_d + (2.0f * sqrtf(best_d) + eta) * eta;
+    s_best[warp][lane] = best;
+    __syncwarp();
+
+    int count = 0;                                   // queued pairs (warp-uniform)
+    // evaluate the last `n` queued pairs, one per lane, and fold the results into the owners' bests
+    auto flush = [&](int n) {
+        const int start = count - n;
+        const bool mine = lane < n;
+        const uint32_t e = mine ? s_queue[warp][start + lane] : (uint32_t)lane;
+        const int owner = (int)(e & 31u);
+        const float ox = __shfl_sync(0xffffffffu, x, owner), oy = __shfl_sync(0xffffffffu, y, owner),
+                    oz = __shfl_sync(0xffffffffu, z, owner);
+        if (mine) {
+            const float4* tp = sorted + 3ll * (long long)(e >> 5);
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            float rx, ry, rz;
+            closest_on_tri(ox, oy, oz, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, rx, ry, rz);
+            const float d = s10_d2(ox, oy, oz, rx, ry, rz);
+            if (d < inf)
+                atomicMin(&s_best[warp][owner], ((unsigned long long)__float_as_uint(d) << 32) |
+                                                   (unsigned long long)(index_offset + __float_as_uint(a.w)));
+        }
+        __syncwarp();
+        const unsigned long long nb = s_best[warp][lane];
+        if (nb < best) {
+            best = nb; best_d = __uint_as_float((uint32_t)(nb >> 32));
+            prune_d = best_d + (2.0f * sqrtf(best_d) + eta) * eta;
+        }
+        count = start;
+        __syncwarp();
+    };
+
+    int sp = 0;
+    int cur = (n_runs > 1) ? 0 : ~0;
+    const float4* nodes4 = reinterpret_cast<const float4*>(nodes);
+    if (n_runs > 0) {
+        while (true) {
+            if (cur < 0) {
+                const long long tri0 = (long long)(~cur) * TRI_LEAF;
+                const float4* lp = sorted + tri0 * 3;
+#pragma unroll
+                for (int i = 0; i < TRI_LEAF; ++i) {
+                    const float4 a = __ldg(lp + 3 * i), b = __ldg(lp + 3 * i + 1), c = __ldg(lp + 3 * i + 2);
+                    if (a.x < inf) {                                        // warp-uniform (run padding)
+                        // a sphere about the centroid (radius b.w, rounded up at build time) holds the triangle:
+                        // (|q - centroid| - r)^2 bounds the S9 distance from below (up to eta, as for nodes;
+                        // the 2e-6 shrink covers the rounding of |q - centroid|)
+                        // the triangle's own box bounds the S9 distance from below (up to eta, as for nodes).
+                        // (A bounding-sphere test queues 7x fewer pairs but its sqrt made the walk 10 % slower.)
+                        const float lb = box_lower_bound(x, y, z, fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y),
+                                                         fminf(fminf(a.z, b.z), c.z), fmaxf(fmaxf(a.x, b.x), c.x),
+                                                         fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z));
+                        const bool want = active && !(lb * BVH_SHRINK > prune_d);
+                        const unsigned m = __ballot_sync(0xffffffffu, want);
+                        if (want) s_queue[warp][count + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)(tri0 + i) << 5) | (uint32_t)lane;
+                        count += __popc(m);
+                    }
+                }
+                __syncwarp();
+                while (count >= 32) flush(32);
+            } else {
+                const float4 n0 = __ldg(nodes4 + 4 * (long long)cur), n1 = __ldg(nodes4 + 4 * (long long)cur + 1);
+                const float4 n2 = __ldg(nodes4 + 4 * (long long)cur + 2), n3 = __ldg(nodes4 + 4 * (long long)cur + 3);
+                const float bl = box_lower_bound(x, y, z, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+                const float br = box_lower_bound(x, y, z, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+                const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+                const bool wl = active && !(bl * BVH_SHRINK > prune_d) && bl < inf;
+                const bool wr = active && !(br * BVH_SHRINK > prune_d) && br < inf;
+                const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
+                if (ml != 0u && mr != 0u) {
+                    const unsigned pl = __ballot_sync(0xffffffffu, wl && (!wr || bl <= br));
+                    const bool left_first = 2 * __popc(pl) >= __popc(ml | mr);
+                    const float fb = left_first ? (wr ? br : inf) : (wl ? bl : inf);
+                    const unsigned fmin = __reduce_min_sync(0xffffffffu, __float_as_uint(fb));
+                    if (lane == 0 && sp < BVH_STACK) {
+                        s_ref[warp][sp] = left_first ? right : left;
+                        s_bound[warp][sp] = __uint_as_float(fmin);
+                    }
+                    if (sp < BVH_STACK) ++sp;
+                    __syncwarp();
+                    cur = left_first ? left : right;
+                    continue;
+                }
+                if (ml != 0u) { cur = left; continue; }
+                if (mr != 0u) { cur = right; continue; }
+            }
+            // before popping, settle the queue if a parked subtree might be pruned by what it holds
+            bool found = false;
+            while (sp > 0) {
+                --sp;
+                const float pb = s_bound[warp][sp];
+                const int pr = s_ref[warp][sp];
+                if (__ballot_sync(0xffffffffu, active && !(pb * BVH_SHRINK > prune_d)) != 0u) {
+                    cur = pr; found = true; break;
+                }
+            }
+            __syncwarp();
+            if (!found) break;
+        }
+        while (count > 0) flush(count < 32 ? count : 32);
+    }
+    if (active) keys[t] = best;
+    if (FUSED) {
+        // K3 + K4 for this thread's query (functions/general.py:299-306, :160-181); the target is the
+        // closest point on the winning triangle, recomputed from the original-order corners (S9)
+        double acc[MOM];
+#pragma unroll
+        for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
+        if (active && best != KEY_NONE) {
+            const long long j = (long long)(uint32_t)(best & 0xFFFFFFFFull) - base_off;
+            const float4 a0 = tris4[3 * j], b0 = tris4[3 * j + 1], c0 = tris4[3 * j + 2];
+            float wx, wy, wz;
+            closest_on_tri(x, y, z, a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, c0.x, c0.y, c0.z, wx, wy, wz);
+            float wqx, wqy, wqz, w1x, w1y, w1z;
+            s1_matvec(st->mw_base, x, y, z, wqx, wqy, wqz);
+            s1_matvec(st->mw_base, wx, wy, wz, w1x, w1y, w1z);
+            const double dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+            if (dist < thresh) {
+                float bx, by, bz;
+                s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);
+                moments_add(acc, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2]);
+            }
+        }
+        block_reduce_moments<SURF_THREADS>(acc, partials);
     }
 }
 

@@ -590,8 +590,8 @@ def test_surface_stepwise_parity(name):
 
 
 def test_surface_packet_walk_equals_per_thread_walk_and_fused_iteration():
-    """200k queries vs a 100k-vertex / 200k-triangle mesh: the warp-packet walk (default), the
-    per-thread walk (nn_variant 10) and the fused iteration kernel agree -- same keys bit for bit,
+    """200k queries vs a 100k-vertex / 200k-triangle mesh: the deferred warp-packet walk (default), the
+    eager packet walk (nn_variant 11), the per-thread walk (nn_variant 10) and the fused kernels agree -- same keys bit for bit,
     same kept-pair counts every iteration, poses equal up to the fp64 summation order."""
     v, t = meshgen.bunny_like_mesh(100_000, 95)
     tri = meshgen.triangle_corners(v, t)
@@ -599,19 +599,20 @@ def test_surface_packet_walk_equals_per_thread_walk_and_fused_iteration():
     rng = np.random.default_rng(97)
     q[rng.choice(200_000, 2000, replace=False)] = ((rng.random((2000, 3)) - 0.5) * 5).astype(np.float32)  # outliers
     out = {}
-    for variant in (0, 10):
+    for variant in (0, 11, 10):
         with IcpEngine(nn_mode=2, thresh=0.5, use_target=False, nn_variant=variant) as e:
             e.set_base_triangles(tri)
             e.set_moving(q)
             e.set_matrices(np.eye(4), np.eye(4))
             idx, d2 = e.nn()
-            done, conv, recs = e.run(6)              # variant 0: fused kernel; variant 10: K1 + walk + K3/K4
+            done, conv, recs = e.run(6)              # 0: fused deferred walk; 11: fused eager walk; 10: K1 + per-thread walk + K3/K4
             idx_after, d2_after = e.nn()             # warm-started search under the final pose
             out[variant] = (idx, d2, [r.pairs for r in recs], e.matrix_world(), idx_after, d2_after)
     a, b = out[0], out[10]
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
-    assert a[2] == b[2]
-    np.testing.assert_allclose(a[3], b[3], atol=2e-6)
+    for other in (out[11], out[10]):
+        assert np.array_equal(a[0], other[0]) and np.array_equal(a[1].view(np.uint32), other[1].view(np.uint32))
+        assert a[2] == other[2]
+        np.testing.assert_allclose(a[3], other[3], atol=2e-6)
     # spot-check the packet walk against the CPU oracle
     sel = rng.choice(200_000, 1500, replace=False)
     oi, od, _ = orc.nn_surface_bruteforce(q[sel], tri)
