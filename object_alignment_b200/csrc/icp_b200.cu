@@ -740,6 +740,7 @@ struct icp_handle {
     float* d_slab_etiles = nullptr;        // [tile][x|y|z|original index][1024], same order
     CylTileHdr* d_slab_hdrs = nullptr;
     int slab_axes = 0;
+    bool slots_stale = false;              // d_mov_slots must be re-gathered (same slot order, new coordinates)
     int slab_order = -1;                   // -1 not built, 0 sorted along a inside a tile, 1 Morton order inside a tile
     // spatial index (nn_mode == ICP_NN_BVH), built lazily from d_base4
     BvhNode* d_bvh_nodes = nullptr;
@@ -1306,7 +1307,17 @@ int launch_nn_bvh(icp_handle* h, long long n_q)
 int ensure_query_order(icp_handle* h, long long n_q)
 {
     const int stride = h->prm.stride > 1 ? h->prm.stride : 1;
-    if (h->order_valid && h->order_stride == stride) return ICP_OK;
+    if (h->order_valid && h->order_stride == stride) {
+        if (h->slots_stale && n_q > 0) {      // new coordinates, same slot order (icp_set_moving)
+            k_gather_mov_slots<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(
+                h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, h->d_slot_pos, n_q, h->d_mov_slots);
+            h->launches += 1;
+            CUDA_TRY(h, cudaGetLastError());
+        }
+        h->slots_stale = false;
+        return ICP_OK;
+    }
+    h->slots_stale = false;
     h->warm_valid = false;
     if (n_q > h->order_capacity || !h->d_slot_pos) {
         if (h->d_slot_pos) cudaFree(h->d_slot_pos);
@@ -1885,9 +1896,18 @@ int icp_set_moving(icp_handle* h, const float* xyz, int64_t n_vertices, const in
     if (rc) return rc;
     if (n_vertices > 0)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_mov, xyz, (size_t)n_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    // Same vertex count and no mask: this is normally the same mesh again (the operator re-uploads per
+    // call), so the Morton slot order and the previous winners are kept -- any order and any real base
+    // vertex / triangle as seed give the exact result, a stale one only costs speed -- and only the
+    // slot-ordered copy of the coordinates is refreshed.
+    const bool same_shape = h->have_moving && h->order_valid && n_vertices == h->n_vertices && !vlist && !h->has_vlist;
     h->n_vertices = n_vertices;
-    h->order_valid = false;
-    h->warm_valid = false;
+    if (same_shape) {
+        h->slots_stale = true;
+    } else {
+        h->order_valid = false;
+        h->warm_valid = false;
+    }
     h->has_vlist = vlist != nullptr;
     h->n_vlist = n_vlist;
     // moments are accumulated about the first vertex of the (replicated) moving array, so that

@@ -418,6 +418,47 @@ def test_bvh_warm_start_stays_exact_over_iterations():
             np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(res["A"], res["B"]), atol=1e-10)
 
 
+@pytest.mark.parametrize("mode", ["bvh", "surface"])
+def test_tree_modes_keep_slot_order_and_seeds_across_same_shape_uploads(mode):
+    """icp_set_moving with the same vertex count keeps the Morton slot order and the previous winners
+    (only the slot-ordered coordinates are refreshed).  A stale order and stale seeds may only cost
+    speed: the same mesh re-uploaded, an unrelated cloud of the same count, and a step() in between
+    must all still give the oracle's answer."""
+    if mode == "bvh":
+        cfg = meshgen.config_cloud(20_000, 40_000, 73, 74)
+        base, mov = cfg["base"], cfg["moving"]
+        set_base = lambda e: e.set_base(base)
+        oracle = lambda q: orc.nn_bruteforce(q, base)[:2]
+        kw = dict(nn_mode=1)
+    else:
+        v, t = meshgen.bunny_like_mesh(8_000, 75)
+        tri = meshgen.triangle_corners(v, t)
+        mov = meshgen.apply_rigid(meshgen.bunny_like(6_000, 76, noise=2e-3), 3.0, (0.02, -0.01, 0.03))
+        set_base = lambda e: e.set_base_triangles(tri)
+        oracle = lambda q: orc.nn_surface_bruteforce(q, tri)[:2]
+        kw = dict(nn_mode=2)
+    other = _rand_cloud(mov.shape[0], 77, 0.8)
+    with IcpEngine(thresh=1e9, use_target=False, **kw) as e:
+        set_base(e)
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        for q in (mov, mov, other, mov):
+            e.set_moving(q)                          # same count: order and seeds are kept
+            e.set_matrices(np.eye(4), np.eye(4))
+            idx, d2 = e.nn()
+            oi, od = oracle(q)
+            assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+            e.step()                                 # fused iteration on the refreshed slots
+        e.set_moving(other)
+        e.set_matrices(np.eye(4), np.eye(4))
+        M, st = e.step()                             # fused kernel straight after a stale-order upload
+        assert st.pairs == other.shape[0]
+        e.set_matrices(np.eye(4), np.eye(4))
+        idx, d2 = e.nn()
+        oi, od = oracle(other)
+        assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+
+
 @pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36, 40, 41, 42])
 def test_bruteforce_seeded_passes_stay_exact(variant):
     """From the second pass on the brute-force filter kernel starts its running minimum from the
