@@ -72,4 +72,38 @@ __device__ __forceinline__ void block_reduce_moments(const double* acc, double* 
     }
 }
 
+// Epilogue of the fused search kernels: one kept pair (or none) per thread -> partials[blockIdx.x][MOM].
+// Each moment is formed and warp-summed on the spot instead of living in a 20-double per-thread
+// accumulator, so the fp64 vector does not set the register count (and the occupancy) of the walk.
+template <int THREADS>
+__device__ __forceinline__ void fused_pair_moments(bool keep, float ax, float ay, float az, float bx, float by,
+                                                   float bz, double dist, double s0, double s1, double s2,
+                                                   double* __restrict__ partials)
+{
+    __shared__ double sh[THREADS / 32][MOM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double k = keep ? 1.0 : 0.0;
+    const double a0 = keep ? (double)ax - s0 : 0.0, a1 = keep ? (double)ay - s1 : 0.0, a2 = keep ? (double)az - s2 : 0.0;
+    const double b0 = keep ? (double)bx - s0 : 0.0, b1 = keep ? (double)by - s1 : 0.0, b2 = keep ? (double)bz - s2 : 0.0;
+    const double d = keep ? dist : 0.0;
+#define ICP_MOM_TERM(i, expr) { const double v_ = warp_sum(expr); if (lane == 0) sh[warp][i] = v_; }
+    ICP_MOM_TERM(0, k)
+    ICP_MOM_TERM(1, a0) ICP_MOM_TERM(2, a1) ICP_MOM_TERM(3, a2)
+    ICP_MOM_TERM(4, b0) ICP_MOM_TERM(5, b1) ICP_MOM_TERM(6, b2)
+    ICP_MOM_TERM(7, b0 * a0) ICP_MOM_TERM(8, b0 * a1) ICP_MOM_TERM(9, b0 * a2)
+    ICP_MOM_TERM(10, b1 * a0) ICP_MOM_TERM(11, b1 * a1) ICP_MOM_TERM(12, b1 * a2)
+    ICP_MOM_TERM(13, b2 * a0) ICP_MOM_TERM(14, b2 * a1) ICP_MOM_TERM(15, b2 * a2)
+    ICP_MOM_TERM(16, a0 * a0 + a1 * a1 + a2 * a2)
+    ICP_MOM_TERM(17, b0 * b0 + b1 * b1 + b2 * b2)
+    ICP_MOM_TERM(18, d)
+    ICP_MOM_TERM(19, d * d)
+#undef ICP_MOM_TERM
+    __syncthreads();
+    if (threadIdx.x < MOM) {
+        double v = 0.0;
+        for (int w = 0; w < THREADS / 32; ++w) v += sh[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * MOM + threadIdx.x] = v;
+    }
+}
+
 }  // namespace icp

@@ -23,7 +23,10 @@
 
 namespace icp {
 
-constexpr int BVH_LEAF = 8;
+#ifndef ICP_BVH_LEAF
+#define ICP_BVH_LEAF 8
+#endif
+constexpr int BVH_LEAF = ICP_BVH_LEAF;
 constexpr int BVH_STACK = 96;   // >= 63 code bits + 32 tie-break bits of radix-tree depth
 
 __device__ __forceinline__ uint64_t morton_expand21(uint32_t v)
@@ -450,21 +453,20 @@ k_nn_bvh_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ so
     }
     if (FUSED) {
         // K3 + K4 for this thread's query (functions/general.py:299-306, :160-181)
-        double acc[MOM];
-#pragma unroll
-        for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
+        bool keep = false;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        double dist = 0.0;
         if (active && best != KEY_NONE) {
             float wqx, wqy, wqz, w1x, w1y, w1z;
             s1_matvec(st->mw_base, x, y, z, wqx, wqy, wqz);
             s1_matvec(st->mw_base, wx, wy, wz, w1x, w1y, w1z);
-            const double dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+            dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
             if (dist < thresh) {
-                float bx, by, bz;
                 s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);
-                moments_add(acc, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2]);
+                keep = true;
             }
         }
-        block_reduce_moments<PKT_THREADS>(acc, partials);
+        fused_pair_moments<PKT_THREADS>(keep, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2], partials);
     }
 }
 

@@ -369,21 +369,20 @@ k_nn_surface_packet(const BvhNode* __restrict__ nodes, const float4* __restrict_
     if (active) keys[t] = best;
     if (FUSED) {
         // K3 + K4 for this thread's query (functions/general.py:299-306, :160-181)
-        double acc[MOM];
-#pragma unroll
-        for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
+        bool keep = false;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        double dist = 0.0;
         if (active && best != KEY_NONE) {
             float wqx, wqy, wqz, w1x, w1y, w1z;
             s1_matvec(st->mw_base, x, y, z, wqx, wqy, wqz);
             s1_matvec(st->mw_base, wx, wy, wz, w1x, w1y, w1z);
-            const double dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+            dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
             if (dist < thresh) {
-                float bx, by, bz;
                 s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);
-                moments_add(acc, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2]);
+                keep = true;
             }
         }
-        block_reduce_moments<SURF_THREADS>(acc, partials);
+        fused_pair_moments<SURF_THREADS>(keep, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2], partials);
     }
 }
 
@@ -400,7 +399,7 @@ k_nn_surface_packet(const BvhNode* __restrict__ nodes, const float4* __restrict_
 constexpr int SURF_QCAP = 32 + 32 * TRI_LEAF;     // queued pairs before a flush + one leaf's worth
 
 template <bool FUSED>
-__global__ void __launch_bounds__(SURF_BOUNDS)
+__global__ void __launch_bounds__(SURF_BOUNDS, 1024 / SURF_BOUNDS)      // <= 64 registers: 32 one-warp CTAs per SM
 k_nn_surface_defer(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
                    const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
                    const DevState* __restrict__ st, const float4* __restrict__ mov_slots,
@@ -551,9 +550,9 @@ k_nn_surface_defer(const BvhNode* __restrict__ nodes, const float4* __restrict__
     if (FUSED) {
         // K3 + K4 for this thread's query (functions/general.py:299-306, :160-181); the target is the
         // closest point on the winning triangle, recomputed from the original-order corners (S9)
-        double acc[MOM];
-#pragma unroll
-        for (int i = 0; i < MOM; ++i) acc[i] = 0.0;
+        bool keep = false;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        double dist = 0.0;
         if (active && best != KEY_NONE) {
             const long long j = (long long)(uint32_t)(best & 0xFFFFFFFFull) - base_off;
             const float4 a0 = tris4[3 * j], b0 = tris4[3 * j + 1], c0 = tris4[3 * j + 2];
@@ -562,14 +561,13 @@ k_nn_surface_defer(const BvhNode* __restrict__ nodes, const float4* __restrict__
             float wqx, wqy, wqz, w1x, w1y, w1z;
             s1_matvec(st->mw_base, x, y, z, wqx, wqy, wqz);
             s1_matvec(st->mw_base, wx, wy, wz, w1x, w1y, w1z);
-            const double dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+            dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
             if (dist < thresh) {
-                float bx, by, bz;
                 s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);
-                moments_add(acc, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2]);
+                keep = true;
             }
         }
-        block_reduce_moments<SURF_THREADS>(acc, partials);
+        fused_pair_moments<SURF_THREADS>(keep, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2], partials);
     }
 }
 
