@@ -330,9 +330,13 @@ k_nn_bvh(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, i
 // (-DICP_PKT_THREADS=32) was 10 % faster on the surface walk but faulted in the vertex walk
 // (compute-sanitizer: out-of-range node reference) and is NOT supported until that is understood.
 constexpr int PKT_THREADS = ICP_PKT_THREADS;
+#ifndef ICP_BVH_RESIDENT
+#define ICP_BVH_RESIDENT 1280      // resident threads per SM the walk is compiled for (<= 48 registers; the fused
+                                   // kernel needs 46).  Measured at C3: 1280 -> 0.44 ms, 1536 -> 0.46, 2048 -> 0.48 (spills)
+#endif
 
 template <bool FUSED, bool COUNT>
-__global__ void __launch_bounds__(PKT_THREADS)
+__global__ void __launch_bounds__(PKT_THREADS, ICP_BVH_RESIDENT / PKT_THREADS)
 k_nn_bvh_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
                 const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
                 const DevState* __restrict__ st, const float4* __restrict__ mov_slots,

@@ -22,16 +22,21 @@ namespace icp {
 
 constexpr int TRI_LEAF = 4;
 
-// One warp per CTA for the surface walks: a CTA's registers are released only when its slowest warp
-// has finished, and the surface walk's tail is long (ncu: 20 % of the samples waited in the epilogue
-// barrier with 4 warps per CTA).  The kernels are COMPILED for up to 64 threads: with
-// __launch_bounds__(32) ptxas drops the warp syncs around the shared stack (it treats the CTA as one
-// converged warp), the votes then see a diverged subset and the walk follows garbage references
-// (caught by compute-sanitizer in the vertex walk).
+// Small CTAs for the surface walks: a CTA's registers are released only when its slowest warp has
+// finished, and the surface walk's tail is long (ncu: 20 % of the samples waited in the epilogue
+// barrier with 4 warps per CTA).  Two warps per CTA at <= 48 registers measured best (40 resident
+// warps; one-warp CTAs are capped at 32 per SM).  The kernels are never COMPILED for fewer than 64
+// threads: with __launch_bounds__(32) ptxas drops the warp syncs around the shared stack (it treats
+// the CTA as one converged warp), the votes then see a diverged subset and the walk follows garbage
+// references (caught by compute-sanitizer in the vertex walk).
 #ifndef ICP_SURF_THREADS
-#define ICP_SURF_THREADS 32
+#define ICP_SURF_THREADS 64
 #endif
 constexpr int SURF_THREADS = ICP_SURF_THREADS;
+#ifndef ICP_SURF_RESIDENT
+#define ICP_SURF_RESIDENT 1280     // resident threads per SM the deferred walk is compiled for (<= 48 registers, 40 B of
+                                   // spills).  Measured at C3s: 64 threads / 1280 -> 1.47 ms, 32 / 1024 -> 1.58, 64 / 1024 -> 1.61
+#endif
 constexpr int SURF_BOUNDS = SURF_THREADS < 64 ? 64 : SURF_THREADS;
 constexpr int SURF_WARPS = (SURF_THREADS + 31) / 32;
 
@@ -399,7 +404,7 @@ k_nn_surface_packet(const BvhNode* __restrict__ nodes, const float4* __restrict_
 constexpr int SURF_QCAP = 32 + 32 * TRI_LEAF;     // queued pairs before a flush + one leaf's worth
 
 template <bool FUSED>
-__global__ void __launch_bounds__(SURF_BOUNDS, 1024 / SURF_BOUNDS)      // <= 64 registers: 32 one-warp CTAs per SM
+__global__ void __launch_bounds__(SURF_BOUNDS, ICP_SURF_RESIDENT / SURF_BOUNDS)
 k_nn_surface_defer(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
                    const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
                    const DevState* __restrict__ st, const float4* __restrict__ mov_slots,
