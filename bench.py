@@ -347,7 +347,7 @@ def run_ours(args, rank, world, local_rank):
     if nn_mode != 0:
         line_roofline = bvh_roofline(m // (world if shard_q else 1), n_local, nn_avg_ms, hbm_peak_of(peaks), args.workload)
         if surface:
-            line_roofline["kernel"] = "k_nn_surface_packet<fused>"
+            line_roofline["kernel"] = "k_nn_surface_defer<fused>"
     sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
     pairs_per_s = m * n_local / (nn_avg_ms * 1e-3) if nn_avg_ms > 0 else 0.0
     cyc_per_pair = 148 * 4 * 32 * sm_hz * 1e6 / pairs_per_s if pairs_per_s else None
