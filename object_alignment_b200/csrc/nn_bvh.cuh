@@ -353,7 +353,6 @@ k_nn_bvh_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ so
     const float inf = __int_as_float(0x7f800000);
 
     float x = 0.f, y = 0.f, z = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    float wx = 0.f, wy = 0.f, wz = 0.f;                 // winner's coordinates (FUSED epilogue)
     unsigned long long best = KEY_NONE;
     if (active) {
         if (FUSED) {
@@ -368,10 +367,7 @@ k_nn_bvh_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ so
                 if (old != KEY_NONE && j >= 0 && j < n_local) {
                     const float4 b = base4[j];
                     const float d = s4_d2(x, y, z, b.x, b.y, b.z);
-                    if (d < inf) {
-                        best = ((unsigned long long)__float_as_uint(d) << 32) | (old & 0xFFFFFFFFull);
-                        wx = b.x; wy = b.y; wz = b.z;
-                    }
+                    if (d < inf) best = ((unsigned long long)__float_as_uint(d) << 32) | (old & 0xFFFFFFFFull);
                 }
             }
         } else {
@@ -390,19 +386,21 @@ k_nn_bvh_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ so
             if (cur < 0) {
                 const float4* lp = sorted + (long long)(~cur) * BVH_LEAF;
                 if (COUNT) ++c_leaf;
+                // branch-free: the smallest 64-bit key of the run, then one compare with the lane's best.
+                // d >= 0, so its bits order like its value; padding (+inf) and NaN are rejected on the
+                // minimum.  The winner's coordinates are fetched once, in the epilogue.
+                unsigned long long kmin = KEY_NONE;
 #pragma unroll
                 for (int i = 0; i < BVH_LEAF; ++i) {
                     const float4 b = __ldg(lp + i);                   // warp-uniform address
                     const float d = s4_d2(x, y, z, b.x, b.y, b.z);
-                    if (d <= best_d && d < inf && active) {            // rare once the bound is tight
-                        const unsigned long long k =
-                            ((unsigned long long)__float_as_uint(d) << 32) |
-                            (unsigned long long)(index_offset + __float_as_uint(b.w));
-                        if (k < best) {
-                            best = k; best_d = d;
-                            if (FUSED) { wx = b.x; wy = b.y; wz = b.z; }
-                        }
-                    }
+                    const unsigned long long k =
+                        ((unsigned long long)__float_as_uint(d) << 32) |
+                        (unsigned long long)(index_offset + __float_as_uint(b.w));
+                    kmin = k < kmin ? k : kmin;
+                }
+                if (kmin < best && (uint32_t)(kmin >> 32) < 0x7f800000u) {
+                    best = kmin; best_d = __uint_as_float((uint32_t)(kmin >> 32));
                 }
             } else {
                 if (COUNT) ++c_inner;
@@ -461,9 +459,10 @@ k_nn_bvh_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ so
         float bx = 0.f, by = 0.f, bz = 0.f;
         double dist = 0.0;
         if (active && best != KEY_NONE) {
+            const float4 w = base4[(long long)(uint32_t)(best & 0xFFFFFFFFull) - base_off];   // the winner
             float wqx, wqy, wqz, w1x, w1y, w1z;
             s1_matvec(st->mw_base, x, y, z, wqx, wqy, wqz);
-            s1_matvec(st->mw_base, wx, wy, wz, w1x, w1y, w1z);
+            s1_matvec(st->mw_base, w.x, w.y, w.z, w1x, w1y, w1z);
             dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
             if (dist < thresh) {
                 s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);
