@@ -450,11 +450,11 @@ def hbm_peak_of(peaks):
 
 def bvh_roofline(m, n_local, avg_ms, hbm_peak, workload):
     """Roofline of k_nn_bvh: compulsory DRAM bytes per launch = queries in (12 B) + keys read and
-    written (16 B) per query + one pass over the tree (64 B per 8-vertex run) and the sorted
+    written (16 B) per query + one pass over the tree (64 B per 16-vertex run) and the sorted
     vertices (16 B each).  The tree walk itself is served by L1/L2 (the index of a 1M-vertex base
     is 24 MB against a 126 MB L2), so this fraction is small by construction; the walk's requested
     bytes are reported beside it."""
-    compulsory = 28.0 * m + (16.0 + 8.0) * n_local
+    compulsory = 28.0 * m + (16.0 + 4.0) * n_local
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "nn_traffic.json"))).get(workload + "_bvh")
@@ -463,10 +463,11 @@ def bvh_roofline(m, n_local, avg_ms, hbm_peak, workload):
     ach = compulsory / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
     return {"kernel": "k_nn_bvh", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
             "frac": ach / hbm_peak if ach else None, "traffic": traffic,
-            "algorithmic": "28 B per query + 24 B per base vertex (index read once)",
+            "algorithmic": "28 B per query + 20 B per base vertex (index read once)",
             "avg_launch_ms": avg_ms, "queries_per_s": m / (avg_ms * 1e-3) if avg_ms > 0 else None,
-            "note": "latency/L2-bound tree walk: ~48 node visits x 64 B + ~8 leaves x 128 B requested per "
-                    "query, served from L1/L2"}
+            "dram_gbs_from_traffic": (traffic / (avg_ms * 1e-3) / 1e9) if (traffic and avg_ms > 0) else None,
+            "note": "latency/issue-bound tree walk: per warp of 32 queries ~100 node visits x 64 B + ~35 leaf "
+                    "visits x 256 B requested, served from L1/L2"}
 
 
 def measure_secondary(cfg, local_rank, mode, steps, warmup):
