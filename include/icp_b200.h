@@ -71,7 +71,12 @@ typedef struct icp_params {
     int32_t nn_mode;         /* icp_nn_mode                                                      */
     int32_t rank;            /* this process's rank among the base shards (0 when single GPU)   */
     int32_t world_size;      /* number of base shards / GPUs (1 when single GPU)                 */
-    int32_t nn_variant;      /* kernel variant for tuning: 0 = library default                   */
+    int32_t nn_variant;      /* kernel variant for tuning / A-B runs; 0 = library default.  Every variant
+                                returns the same keys.  Brute force: 1-6 direct metric, 20-24 expansion
+                                filter, 30-36 cylinder filter, 40-45 slab filter (default for seeded
+                                passes: 42).  BVH: 10 per-thread walk, 11 packet walk without the fused
+                                epilogue.  Surface: 10 per-thread walk, 11 packet walk with eager
+                                triangle tests (default: deferred tests)                          */
     int32_t shard_mode;      /* icp_shard_mode when world_size > 1                               */
 } icp_params;
 
