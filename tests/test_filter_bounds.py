@@ -1,0 +1,120 @@
+"""CPU property test of the brute-force kernels' lower-bound filters (no GPU, no oracle needed).
+
+The slab / cylinder / 3-axis tests of `csrc/nn_bruteforce_slab.cuh` and `nn_bruteforce_cyl.cuh` may
+skip a base vertex only if it can neither win nor tie.  Restated in numpy with the kernels' exact
+fp32 operation order (fma emulated through float64, whose product of two float32 is exact), the
+property checked here is the one the exactness argument rests on ("Error budget"):
+
+    for every query q and EVERY vertex j of a tile, with  best = S4(q, b_j)  (j ties the running best):
+        F1_a(q, j) <= thr1_a,   F1_b(q, j) <= thr1_b      (slab test along either axis)
+        F(q, j)    <= thr_f                               (cylinder test)
+        E3(q, j)   <= thr_3                               (3-axis expansion test)
+
+so a vertex whose exact-metric distance equals (or beats) the current best always reaches the exact
+S4 evaluation.  Data: tiles at unit scale, 800 units from the origin, at 1e-4 and 1e+3 scale, flat and
+needle-shaped tiles, queries inside, near and far from the tile.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+F = np.float32
+
+
+def fma(a, b, c):
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(F)
+
+
+def s4_d2(q, b):
+    dx, dy, dz = (q[..., 0] - b[..., 0]).astype(F), (q[..., 1] - b[..., 1]).astype(F), (q[..., 2] - b[..., 2]).astype(F)
+    return fma(dz, dz, fma(dy, dy, (dx * dx).astype(F)))
+
+
+def tile_planes(pts):
+    """k_build_slab_tiles: centre, centred planes, w2, per-axis squares, b2 (axes a, b, c = x, y, z)."""
+    lo, hi = pts.min(axis=0), pts.max(axis=0)
+    cen = (F(0.5) * lo + F(0.5) * hi).astype(F)
+    p = (pts - cen).astype(F)
+    wa, wb = (p[:, 0] * p[:, 0]).astype(F), (p[:, 1] * p[:, 1]).astype(F)
+    w2 = fma(p[:, 1], p[:, 1], wa)
+    b2 = F(fma(p[:, 2], p[:, 2], w2).max() * F(1.00001))
+    return cen, p, wa, wb, w2, b2
+
+
+def filter_margins(q, pts):
+    """Smallest slack (threshold - bound) over all (query, vertex) pairs, per test, with best = S4(q, b_j)."""
+    cen, p, wa, wb, w2, b2 = tile_planes(pts)
+    Q = q[:, None, :]
+    best = s4_d2(np.broadcast_to(Q, (q.shape[0], pts.shape[0], 3)), np.broadcast_to(pts[None], (q.shape[0], pts.shape[0], 3)))
+    pq = (q - cen).astype(F)                                    # centred query
+    pa, pb, pc = pq[:, 0:1], pq[:, 1:2], pq[:, 2:3]
+    na, nb = (pa * pa).astype(F), (pb * pb).astype(F)
+    # slab_setup
+    nq3_s = fma(pc, pc, (na + nb).astype(F))
+    delta_s = (F(4.0e-6) * (nq3_s + b2).astype(F)).astype(F)
+    thr1_a = ((best + delta_s).astype(F) - na).astype(F)
+    thr1_b = ((best + delta_s).astype(F) - nb).astype(F)
+    f1_a = fma((F(-2.0) * pa).astype(F), p[None, :, 0], wa[None])
+    f1_b = fma((F(-2.0) * pb).astype(F), p[None, :, 1], wb[None])
+    # cyl_setup / cyl_recheck
+    nq2 = fma(pb, pb, (pa * pa).astype(F))
+    nq3 = fma(pc, pc, nq2)
+    delta = (F(4.0e-6) * (nq3 + b2).astype(F)).astype(F)
+    ax, ay, az = (F(-2.0) * pa).astype(F), (F(-2.0) * pb).astype(F), (F(-2.0) * pc).astype(F)
+    thr_f = ((best + delta).astype(F) - nq2).astype(F)
+    thr_3 = (thr_f - (pc * pc).astype(F)).astype(F)
+    f = fma(ay, p[None, :, 1], fma(ax, p[None, :, 0], w2[None]))
+    zc = p[None, :, 2]
+    e3 = fma(zc, (zc + az).astype(F), f)
+    scale = (nq3 + b2).astype(np.float64)                       # s^2-like normaliser of the slack
+    rel = lambda thr, val: float(((thr.astype(np.float64) - val.astype(np.float64)) / scale).min())
+    return dict(slab_a=rel(thr1_a, f1_a), slab_b=rel(thr1_b, f1_b), cyl=rel(thr_f, f), e3=rel(thr_3, e3))
+
+
+def _tile(rng, kind, scale, offset):
+    n = 1024
+    if kind == "blob":
+        pts = rng.standard_normal((n, 3))
+    elif kind == "flat":                      # a surface patch: thin along z
+        pts = rng.standard_normal((n, 3)) * np.array([1.0, 1.0, 0.01])
+    elif kind == "needle":                    # long along x
+        pts = rng.standard_normal((n, 3)) * np.array([5.0, 0.02, 0.02])
+    else:                                     # lattice: many exactly tied distances
+        g = np.arange(10.0)
+        pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+        pts = np.concatenate([pts, pts[:24]])
+    return (pts * 0.07 * scale + offset).astype(F)
+
+
+@pytest.mark.parametrize("kind", ["blob", "flat", "needle", "lattice"])
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1.0, 800.0), (1e-4, 0.0), (1e-4, 0.3), (1e3, -5e4)])
+def test_no_vertex_that_ties_the_best_is_filtered(kind, scale, offset):
+    rng = np.random.default_rng(zlib.crc32(repr((kind, scale, offset)).encode()))
+    pts = _tile(rng, kind, scale, np.array([offset, -0.6 * offset, 0.3 * offset]))
+    cen = pts.mean(axis=0)
+    ext = float(np.abs(pts - cen).max())
+    queries = [
+        pts[rng.integers(0, len(pts), 64)],                                                       # on vertices
+        (pts[rng.integers(0, len(pts), 64)] + rng.standard_normal((64, 3)) * 0.01 * ext),         # near the surface
+        (cen + rng.standard_normal((64, 3)) * ext),                                               # inside the tile
+        (cen + rng.standard_normal((64, 3)) * 30 * ext),                                          # far away
+        (cen + np.array([1.0, 0.0, 0.0]) * ext * rng.uniform(-40, 40, (64, 1))),                  # along one axis
+    ]
+    q = np.concatenate(queries).astype(F)
+    m = filter_margins(q, pts)
+    # every slack is positive; the kernels' delta is 4e-6 (|q'|^2 + B^2) and the analysed need is
+    # 24.5 u s^2 ~ 1.5e-6 s^2 <= 2.9e-6 (|q'|^2 + B^2), so at least ~1e-6 of it must be left over
+    for name, slack in m.items():
+        assert slack > 5e-7, (name, slack)
+
+
+def test_margin_is_not_vacuous():
+    """With delta = 0 the same data does violate the inequalities: the test can fail."""
+    rng = np.random.default_rng(5)
+    pts = _tile(rng, "flat", 1.0, np.array([800.0, -500.0, 300.0]))
+    q = (pts[rng.integers(0, len(pts), 256)] + rng.standard_normal((256, 3)) * 1e-3).astype(F)
+    m = filter_margins(q, pts)
+    # slack is reported relative to (|q'|^2 + B^2); subtracting the 4e-6 the kernels add shows what
+    # the raw rounding error alone would do
+    assert min(m.values()) - 4.0e-6 < 0.0
