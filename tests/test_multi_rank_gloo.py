@@ -100,3 +100,46 @@ def test_sharded_protocol_equals_unsharded(world, tmp_path):
     assert int(z["K"]) == int(ref["keep"].sum())
     np.testing.assert_allclose(z["M"], orc.affine_matrix_from_points_port(ref["A"], ref["B"]),
                                rtol=0, atol=1e-12)
+
+
+def _worker_queries(rank, world, port, out_dir):
+    """ICP_SHARD_QUERIES protocol (tree searches): base replicated, every rank owns a contiguous
+    slice of the query positions; the only exchange is the SUM over the 20 moment doubles, taken
+    about the same reference point (the first moving vertex) on every rank."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from object_alignment_b200 import dist as icpdist
+    from object_alignment_b200 import meshgen, shard_range
+    from oracle import icp_oracle as orc
+
+    dist = icpdist.init_rendezvous("gloo")
+    cfg = meshgen.config_cloud(3001, 4000, 43, 44)
+    mov, base = cfg["moving"], cfg["base"]
+    lo, hi = shard_range(mov.shape[0], rank, world)
+    eye = np.eye(4, dtype=np.float32)
+    res = orc.make_pairs_vec(mov, np.arange(lo, hi), eye, eye, base, 0.5, 1, return_all=True)
+    shift = mov[0].astype(np.float64)                     # shared reference point, not mov[lo]
+    mom = icpdist.allreduce_sum_host(_moments(res["A"], res["B"], shift), dist)
+    M = _solve_from_moments(mom, shift)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "outq.npz"), M=M, K=mom[0])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_query_sharded_protocol_equals_unsharded(world, tmp_path):
+    from object_alignment_b200 import meshgen, shard_range
+    from oracle import icp_oracle as orc
+
+    # the slices tile the query positions exactly, in order
+    cuts = [shard_range(3001, r, world) for r in range(world)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == 3001 and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    mp.spawn(_worker_queries, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    z = np.load(tmp_path / "outq.npz")
+    cfg = meshgen.config_cloud(3001, 4000, 43, 44)
+    eye = np.eye(4, dtype=np.float32)
+    ref = orc.make_pairs_vec(cfg["moving"], np.arange(3001), eye, eye, cfg["base"], 0.5, 1, return_all=True)
+    assert int(z["K"]) == int(ref["keep"].sum())
+    np.testing.assert_allclose(z["M"], orc.affine_matrix_from_points_port(ref["A"], ref["B"]),
+                               rtol=0, atol=1e-12)
