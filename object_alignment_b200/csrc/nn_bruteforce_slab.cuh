@@ -1,34 +1,36 @@
 // nn_bruteforce_slab.cuh -- K2, fourth form: brute-force nearest vertex with a 1-FMA "slab" filter in
-// front of the cylinder filter of nn_bruteforce_cyl.cuh (nn_variant 40..).
+// front of the cylinder filter of nn_bruteforce_cyl.cuh (nn_variant 40..45; the default for seeded passes).
 //
 // Replaces the per-vertex `base_bvh.find_nearest(co_find)` of the reference
 // (functions/general.py:297, nearest-VERTEX variant).  Still O(M N): every
 // (query, base vertex) pair is evaluated, but the hot loop evaluates the weakest useful lower bound
 // of the squared distance, ONE fma per pair:
 //
-//     F1(q, b) = fma(-2 q'a, b'a, w1)        w1 = b'a^2
-//              ~ (q'a - b'a)^2 - q'a^2
+//     F1(q, b) = fma(-2 q's, b's, b's^2)  ~  (q's - b's)^2 - q's^2
 //
-// (a = the axis of largest extent of the shard; primes are coordinates relative to the centre of
-// the 1024-vertex tile the base vertex lives in).  F1 + q'a^2 is the squared distance to the PLANE
-// through b normal to a, which never exceeds the squared distance to b.  A chunk of CH vertices can
-// hold the winner only if
+// where s is the slab axis and primes are coordinates relative to the centre of the 1024-vertex tile
+// the base vertex lives in.  F1 + q's^2 is the squared distance to the PLANE through b normal to s,
+// which never exceeds the squared distance to b.  A chunk of CH vertices can hold the winner only if
 //
-//     chunk_min(F1) <= best_d2 + delta - q'a^2          (best_d2: S4 value of a real vertex)
+//     chunk_min(F1) <= best_d2 + delta - q's^2          (best_d2: S4 value of a real vertex)
 //
-// Tiles are Morton-ordered (compact boxes, small delta) and the vertices INSIDE a tile are sorted
-// along a, so the vertices a query's slab cuts out of a tile sit in two or three adjacent chunks.
+// Tiles carry both candidate axes a and b (the two longest axes of the shard; planes
+// a' | b' | w2 = a'^2 + b'^2 | c' | a'^2 | b'^2) and every (warp, tile) picks, by one ballot, the axis
+// along which its queries are farther from the tile centre: any axis gives a valid bound, that one
+// prunes best.  Tiles are Morton-ordered (compact boxes, small delta); inside a tile the vertices are
+// sorted along a (nn_variant 40..43) or left in Morton order (44, 45) -- no measurable difference.
 // A chunk that triggers is re-tested per query with the packed 2-fma cylinder bound
 // (cyl_chunk_min), and only what survives goes through cyl_recheck (cylinder per vertex, 3-axis
-// expansion, exact S4) -- the same slow path, hence the same bit-identical 64-bit keys, ties to
-// the lowest ORIGINAL index.
+// expansion, exact S4) -- the same slow path as the cylinder kernel, hence the same bit-identical
+// 64-bit keys, ties to the lowest ORIGINAL index.
 //
 // Error budget: F1 has one rounding fewer than the cylinder bound F and the same centring error, so
 // the cylinder kernel's delta = 4e-6 (|q'|^2 + B^2) (>= 33.5 u s^2 against a need of 24.5 u s^2,
-// derivation in DESIGN.md) covers the slab test with room to spare.
+// derivation in DESIGN.md) covers the slab test with room to spare; tests/test_filter_bounds.py
+// checks all four inequalities in numpy with this file's operation order.
 //
 // Issue cost (tools/ubench/pipes2.cu): 1 FFMA2 + 1 FMNMX3 per two pairs = 3.8 cycles per SMSP against
-// 6.7 for the cylinder kernel's 2 FFMA2 + 1 FMNMX3.
+// 6.7 for the cylinder kernel's 2 FFMA2 + 1 FMNMX3.  C3 (1M x 1M): 65.6 ms per pass, 1.52e13 pairs/s.
 #pragma once
 #include "nn_bruteforce_cyl.cuh"
 
@@ -55,7 +57,7 @@ __global__ void k_slab_keys(const float4* __restrict__ base4, const uint32_t* __
     keys[j] = ((unsigned long long)(j / NN_TILE) << 32) | (unsigned long long)orderable_bits(axis_of(b.x, b.y, b.z, axis_a));
 }
 
-// One CTA (256 threads) per tile: like k_build_cyl_tiles plus the w1 plane.
+// One CTA (256 threads) per tile: like k_build_cyl_tiles plus the a'^2 and b'^2 planes.
 __global__ void __launch_bounds__(256)
 k_build_slab_tiles(const float4* __restrict__ base4, const uint32_t* __restrict__ order, long long n,
                    int axis_a, int axis_b, int axis_c, float* __restrict__ ftiles,
