@@ -32,6 +32,7 @@
 #include "nn_bruteforce.cuh"
 #include "nn_bruteforce_cyl.cuh"
 #include "nn_bruteforce_slab.cuh"
+#include "nn_bruteforce_q16.cuh"
 #include "nn_bvh.cuh"
 #include "nn_surface.cuh"
 
@@ -80,7 +81,8 @@ __global__ void k_transform_queries(const DevState* __restrict__ st, const float
                                     float* __restrict__ qz, unsigned long long* keys,
                                     const unsigned long long* warm_src, const float4* __restrict__ base4,
                                     const float4* __restrict__ tris4, long long base_off,
-                                    long long n_local)
+                                    long long n_local, const unsigned long long* prev_global = nullptr,
+                                    float* __restrict__ bound_out = nullptr)
 {
     if (st->converged) return;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,6 +93,24 @@ __global__ void k_transform_queries(const DevState* __restrict__ st, const float
     float wx, wy, wz, x, y, z;
     s1_matvec(st->mw_align, ax, ay, az, wx, wy, wz);
     s1_matvec(st->imx2, wx, wy, wz, x, y, z);
+    if (bound_out != nullptr) {
+        // Base sharded across ranks: this rank's own previous winner can be far from the query (the
+        // global winner lives on another rank), but every rank holds the GLOBAL winner's distance d of
+        // the previous pass (prev_global, after the all-reduce) and that pass's query q_old of this slot
+        // (still in qx/qy/qz).  The same vertex is at most sqrt(d) + |q - q_old| from the new query
+        // (triangle inequality), so nothing farther than that can win or tie: a pruning radius that
+        // needs no coordinate exchange.  (1 + 4e-6) covers the fp32 roundings of d, of this
+        // expression and of the S4 distance the new winner will be compared with.
+        float bd = __int_as_float(0x7f800000);
+        const unsigned long long g = prev_global[t];      // may alias keys (same element, read first)
+        if (g != KEY_NONE) {
+            const float ex = __fsub_rn(x, qx[t]), ey = __fsub_rn(y, qy[t]), ez = __fsub_rn(z, qz[t]);
+            const float dq = sqrtf(__fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex))));
+            const float sr = __fadd_rn(sqrtf(__uint_as_float((uint32_t)(g >> 32))), dq);
+            bd = __fmul_rn(__fmul_rn(sr, sr), 1.000004f);
+        }
+        bound_out[t] = bd;
+    }
     qx[t] = x; qy[t] = y; qz[t] = z;
     unsigned long long key = KEY_NONE;
     if (warm_src) {                                        // may alias keys (same element only)
@@ -742,6 +762,16 @@ struct icp_handle {
     int slab_axes = 0;
     bool slots_stale = false;              // d_mov_slots must be re-gathered (same slot order, new coordinates)
     int slab_order = -1;                   // -1 not built, 0 sorted along a inside a tile, 1 Morton order inside a tile
+    // 16-bit quantised tiles of the q16 kernel (nn_variant 50..): [tile][a|b|c u16 planes, header]
+    uint32_t* d_q16_tiles = nullptr;
+    float* d_q16_etiles = nullptr;         // [tile][x|y|z|original index][1024], same order
+    int q16_axes = 0;
+    int q16_order = -1;                    // -1 not built, 0 sorted along a inside a tile, 1 Morton order inside a tile
+    // base sharded across ranks: squared pruning radius per slot from the GLOBAL previous winner
+    float* d_bound = nullptr;
+    long long bound_capacity = 0;
+    bool bound_active = false;             // the pass being enqueued has a valid d_bound
+    std::vector<const void*> smem_configured;   // kernels whose dynamic-smem limit was raised on THIS device
     // spatial index (nn_mode == ICP_NN_BVH), built lazily from d_base4
     BvhNode* d_bvh_nodes = nullptr;
     float4* d_bvh_sorted = nullptr;
@@ -846,6 +876,18 @@ int ensure(icp_handle* h, T*& ptr, long long& cap, long long need)
     return ICP_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember it per handle
+// (a handle is bound to one device), not per process.
+template <typename K>
+int configure_smem(icp_handle* h, K kern, size_t smem)
+{
+    const void* f = reinterpret_cast<const void*>(kern);
+    for (const void* p : h->smem_configured) if (p == f) return ICP_OK;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->smem_configured.push_back(f);
+    return ICP_OK;
+}
+
 // brute-force variants.  0 (default): query slots in Morton order; the unseeded first pass runs the
 // expansion-filter kernel (or the direct kernel on small shards), every later pass the slab kernel
 // (1-fma plane bound, then the 2-fma cylinder bound, then the exact metric) over Morton-ordered,
@@ -866,7 +908,7 @@ bool uses_slots(const icp_handle* h)
 {
     if (h->prm.nn_mode != ICP_NN_BRUTEFORCE) return true;
     const int v = h->prm.nn_variant;
-    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36) || slab_variant(v);
+    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36) || slab_variant(v) || (v >= 50 && v <= 58);
 }
 
 long long query_count(const icp_handle* h)
@@ -913,11 +955,7 @@ int launch_nn_t(icp_handle* h, long long n_q)
 {
     auto kern = k_nn_bruteforce<R, STAGES, PACKED>;
     const size_t smem = (size_t)STAGES * NN_TILE_BYTES + STAGES * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    { int rc_ = configure_smem(h, kern, smem); if (rc_) return rc_; }
     const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
     // base ranges: enough CTAs for ~8 waves over the chip so the tail is small, but every CTA
     // still streams >= 8 tiles so the TMA ring and the final index recovery are amortised
@@ -973,11 +1011,7 @@ int launch_nn_filter_t(icp_handle* h, long long n_q)
     if (rc) return rc;
     auto kern = k_nn_bruteforce_filter<R, STAGES>;
     const size_t smem = (size_t)STAGES * NNF_TILE_BYTES + STAGES * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    { int rc_ = configure_smem(h, kern, smem); if (rc_) return rc_; }
     const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
@@ -1058,11 +1092,7 @@ int launch_nn_cyl_t(icp_handle* h, long long n_q)
 {
     auto kern = k_nn_bruteforce_cyl<R, STAGES, CH>;
     const size_t smem = (size_t)STAGES * CYL_TILE_BYTES + STAGES * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    { int rc_ = configure_smem(h, kern, smem); if (rc_) return rc_; }
     const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
@@ -1148,11 +1178,7 @@ int launch_nn_slab_t(icp_handle* h, long long n_q)
 {
     auto kern = k_nn_bruteforce_slab<R, STAGES, CH>;
     const size_t smem = (size_t)STAGES * SLAB_TILE_BYTES + 2 * STAGES * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    { int rc_ = configure_smem(h, kern, smem); if (rc_) return rc_; }
     const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
@@ -1174,13 +1200,105 @@ int launch_nn_slab_t(icp_handle* h, long long n_q)
     return ICP_OK;
 }
 
+// q16 tiles: the slab kernel's vertex order (Morton order decides the tile, then a sort along the axis of
+// largest extent inside the tile -- or Morton order inside the tile too), quantised to 16 bits per
+// tile.  One-time per base.
+int build_q16(icp_handle* h, int want_order)
+{
+    if (h->q16_order == want_order) return ICP_OK;
+    for (void* p : {(void*)h->d_q16_tiles, (void*)h->d_q16_etiles}) if (p) cudaFree(p);
+    h->d_q16_tiles = nullptr; h->d_q16_etiles = nullptr;
+    const long long n = h->n_local;
+    if (n > 0) {
+        unsigned long long *codes = nullptr, *codes_out = nullptr;
+        uint32_t *order = nullptr, *order_out = nullptr;
+        float *part = nullptr, *bbox = nullptr;
+        void* temp = nullptr;
+        size_t temp_bytes = 0;
+        const int pb = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
+        const unsigned gn = (unsigned)((n + 255) / 256);
+        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 24));
+        CUDA_TRY(h, cudaMalloc((void**)&bbox, 24));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_tiles, (size_t)h->n_tiles * Q16_TILE_BYTES));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_etiles, (size_t)h->n_tiles * CYL_TILE_BYTES));
+        CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n * 8));
+        CUDA_TRY(h, cudaMalloc((void**)&order, (size_t)n * 4));
+        CUDA_TRY(h, cudaMalloc((void**)&order_out, (size_t)n * 4));
+        k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
+        k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
+        k_morton_codes<<<gn, 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order);
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 64, h->stream));
+        CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
+        // a, b = the two longest axes of the shard (the candidate slab axes), c = the shortest
+        float hb[6];
+        CUDA_TRY(h, cudaMemcpyAsync(hb, bbox, 24, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ext[3];
+        for (int k = 0; k < 3; ++k) { ext[k] = hb[3 + k] - hb[k]; if (!(ext[k] >= 0.0f)) ext[k] = 0.0f; }
+        int a = 0, c = 2;
+        for (int k = 1; k < 3; ++k) if (ext[k] > ext[a]) a = k;
+        for (int k = 1; k >= 0; --k) if (ext[k] < ext[c]) c = k;
+        if (c == a) c = (a + 2) % 3;
+        const int b = 3 - a - c;
+        h->q16_axes = a | (b << 2) | (c << 4);
+        if (want_order == 0) {
+            k_slab_keys<<<gn, 256, 0, h->stream>>>(h->d_base4, order_out, n, a, codes);
+            CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order_out, order, (int)n, 0, 64, h->stream));
+        }
+        k_build_q16_tiles<<<(unsigned)h->n_tiles, 256, 0, h->stream>>>(h->d_base4, want_order == 0 ? order : order_out, n, a, b, c,
+                                                                      h->d_q16_tiles, h->d_q16_etiles);
+        h->launches += 7;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (void* p : {(void*)codes, (void*)codes_out, (void*)order, (void*)order_out, (void*)part, (void*)bbox, temp}) if (p) cudaFree(p);
+    }
+    h->q16_order = want_order;
+    return ICP_OK;
+}
+
+template <int R, int STAGES, int CH>
+int launch_nn_q16_t(icp_handle* h, long long n_q)
+{
+    auto kern = k_nn_bruteforce_q16<R, STAGES, CH>;
+    const size_t smem = (size_t)STAGES * ((Q16_TILE_BYTES + 127) / 128 * 128) + 2 * STAGES * sizeof(uint64_t);
+    { int rc_ = configure_smem(h, kern, smem); if (rc_) return rc_; }
+    const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)h->sm_count * occ;
+    long long want_y = (8 * slots + qb - 1) / qb;
+    long long max_y = std::max<long long>(1, h->n_tiles / 8);
+    long long gy = std::max<long long>(1, std::min(want_y, max_y));
+    int tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy);
+    gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    if (gy > 65535) { gy = 65535; tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy); gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta; }
+    dim3 grid((unsigned)qb, (unsigned)gy);
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_q16_tiles, h->d_q16_etiles, h->q16_axes, h->n_tiles, tiles_per_cta,
+                                                qx, qy, qz, n_q, h->d_keys, h->bound_active ? h->d_bound : nullptr,
+                                                (uint32_t)h->base_off, &h->d_state->converged);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
+
+bool q16_variant(int v) { return v >= 50 && v <= 58; }   // 58 = 50 without the global pruning bound (A/B)
+
 int launch_nn(icp_handle* h, long long n_q)
 {
     if (n_q <= 0 || h->n_tiles <= 0) return ICP_OK;
     int variant = h->prm.nn_variant;
+    if (q16_variant(variant) && !h->bf_warm_active) variant = 0;       // the q16 kernel needs a seed: cold pass below
     if (variant == 0) {
-        if (h->bf_warm_active && h->n_tiles >= 16) variant = 42;       // seeded: slab + cylinder filter kernel
+        if (h->bf_warm_active && h->n_tiles >= 16) variant = 50;       // seeded: 16-bit slab kernel
         else variant = h->n_tiles >= 256 ? 20 : 2;                     // cold: filter / direct kernel
+    }
+    if (q16_variant(variant)) {
+        int rc = build_q16(h, (variant == 54 || variant == 55) ? 1 : 0);
+        if (rc) return rc;
     }
     if (variant >= 20 && variant <= 29) {
         int rc = build_filter(h);      // outside the profiled region (one-time)
@@ -1196,6 +1314,12 @@ int launch_nn(icp_handle* h, long long n_q)
     }
     ProfScope ps(h, 0);
     switch (variant) {
+        case 50: case 54: case 58: return launch_nn_q16_t<4, 4, 64>(h, n_q);
+        case 51: case 55: return launch_nn_q16_t<8, 4, 64>(h, n_q);
+        case 52: return launch_nn_q16_t<4, 4, 128>(h, n_q);
+        case 53: return launch_nn_q16_t<8, 4, 128>(h, n_q);
+        case 56: return launch_nn_q16_t<2, 4, 64>(h, n_q);
+        case 57: return launch_nn_q16_t<4, 4, 32>(h, n_q);
         case 40: return launch_nn_slab_t<4, 3, 32>(h, n_q);
         case 41: return launch_nn_slab_t<8, 3, 32>(h, n_q);
         case 42: return launch_nn_slab_t<4, 3, 64>(h, n_q);
@@ -1436,6 +1560,12 @@ int enqueue_nn(icp_handle* h, long long n_q)
             warm_src = sharded_base ? h->d_keys_local : h->d_keys;
     }
     h->bf_warm_active = !tree && warm_src != nullptr;
+    // sharded base: d_keys still hold the previous pass's GLOBAL winners and d_q its queries
+    h->bound_active = h->bf_warm_active && sharded_base && h->prm.nn_variant != 58;
+    if (h->bound_active) {
+        rc = ensure(h, h->d_bound, h->bound_capacity, n_q);
+        if (rc) return rc;
+    }
     {
         ProfScope ps(h, 3);
         k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
@@ -1444,7 +1574,7 @@ int enqueue_nn(icp_handle* h, long long n_q)
                 h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q,
                 slots ? h->d_slot_pos : nullptr, qx, qy, qz, h->d_keys,
                 warm_src, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off,
-                h->n_local);
+                h->n_local, h->bound_active ? h->d_keys : nullptr, h->bound_active ? h->d_bound : nullptr);
         h->launches += 2;
     }
     if (h->surface != (h->prm.nn_mode == ICP_NN_SURFACE))
@@ -1760,7 +1890,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1798,6 +1928,7 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
     h->filter_built = false;
     h->cyl_sorted = -1;
     h->slab_order = -1;
+    h->q16_order = -1;
     h->warm_valid = false;
     h->bf_warm_valid = false;
     if (n_local > 0) {

@@ -1,0 +1,371 @@
+// nn_bruteforce_q16.cuh -- K2, fifth form: brute-force nearest vertex whose hot loop is ONE integer
+// instruction per two (query, base vertex) pairs (nn_variant 50..57; the default for seeded passes).
+//
+// Replaces the per-vertex `base_bvh.find_nearest(co_find)` of the reference
+// (functions/general.py:297, nearest-VERTEX variant).  Still O(M N): every pair is
+// evaluated, against the weakest useful lower bound of the distance -- the distance along ONE axis:
+//
+//     |q_s - b_s| <= T        T = sqrt(best_d2) (1 + eps),  best_d2 the S4 value of a real vertex
+//
+// A vertex can beat or tie the running best only if it passes this test on every axis: S4 computes
+// d2 = fma(dz,dz, fma(dy,dy, dx*dx)) with dx = fl(q.x - b.x), every partial result is >= fl(dx*dx) by
+// monotonicity of rounding, so d2 <= best implies |dx| <= sqrt(best)(1 + 2^-23) (same for y, z).
+//
+// The slab kernel (nn_bruteforce_slab.cuh) spends an FFMA2 and an FMNMX3 per two pairs on this test
+// and the two pipes overlap badly (ncu: fma 44 %, alu 48 %).  Here the coordinates of a tile are
+// QUANTISED to 16 bits inside the tile's own bounding box and packed two vertices per 32-bit word,
+// and the interval test turns into the classic unsigned range check
+//
+//     u in [lo, hi]   <=>   (u - lo) mod 2^16  <  hi - lo + 1 = W
+//
+// folded into a running per-chunk minimum by the DPX instruction VIADDMNMX.U16x2:
+//
+//     acc = min16x2( u_word + (-lo, -lo), acc )           acc starts at (W, W)
+//
+// After a chunk, acc != (W, W) means some vertex of the chunk lies inside the slab.  One ALU-pipe
+// instruction per two pairs, no fp32 work at all, a tile is 6 KB instead of 24 KB.  Quantisation is
+// CONSERVATIVE: u = round((b - lo_tile) * inv_tile) is off by at most half a step, the query interval
+// is widened by 2 steps plus the fp32 rounding of its own evaluation, so a vertex inside the real
+// interval is always inside the integer one (tests/test_filter_bounds.py restates it in numpy).
+//
+// A chunk that triggers for a query is re-tested per vertex with the 3-axis integer box (three
+// VIADDMNMX + one VIMNMX3.U16x2 per two vertices), and only vertices inside the box get the exact S4
+// metric from the exact tile in global memory -- so the 64-bit keys are bit-identical to the direct
+// kernel's, ties to the lowest ORIGINAL index.
+#pragma once
+#include "nn_bruteforce_slab.cuh"
+
+namespace icp {
+
+constexpr int Q16_PLANE_WORDS = NN_TILE / 2;                  // two vertices per word
+constexpr int Q16_HDR_WORDS = 8;
+constexpr int Q16_TILE_WORDS = 3 * Q16_PLANE_WORDS + Q16_HDR_WORDS;   // a | b | c planes + header
+constexpr int Q16_TILE_BYTES = Q16_TILE_WORDS * 4;            // 6176 B per TMA bulk copy
+constexpr int Q16_WARPS = NN_THREADS / 32;
+constexpr float Q16_LEVELS = 65534.0f;                        // 65535 is the padding value (never inside)
+
+// header at the end of every tile (permuted axes a, b, c): lower corner, steps per unit, centre
+struct Q16Hdr {
+    float lo_a, lo_b, lo_c;
+    float inv_a, inv_b, inv_c;
+    float cen_a, cen_b;
+};
+static_assert(sizeof(Q16Hdr) == Q16_HDR_WORDS * 4, "Q16Hdr layout");
+
+// One CTA (256 threads) per tile.  `order` maps a sorted position to the original vertex index.
+__global__ void __launch_bounds__(256)
+k_build_q16_tiles(const float4* __restrict__ base4, const uint32_t* __restrict__ order, long long n,
+                  int axis_a, int axis_b, int axis_c, uint32_t* __restrict__ qtiles,
+                  float* __restrict__ etiles)
+{
+    __shared__ float red[6][8];
+    __shared__ float box[6];
+    __shared__ unsigned short us[3][NN_TILE];
+    const float inf = __int_as_float(0x7f800000);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long t = blockIdx.x;
+    float x[4], y[4], z[4];
+    uint32_t oi[4];
+    bool fin[4];
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long j = t * NN_TILE + k * 256 + tid;
+        x[k] = y[k] = z[k] = inf;
+        oi[k] = 0xFFFFFFFFu;
+        fin[k] = false;
+        if (j < n) {
+            const uint32_t o = order[j];
+            const float4 b = base4[o];
+            x[k] = b.x; y[k] = b.y; z[k] = b.z; oi[k] = o;
+            fin[k] = (fabsf(b.x) < inf) && (fabsf(b.y) < inf) && (fabsf(b.z) < inf);
+            if (fin[k]) {
+                lo[0] = fminf(lo[0], b.x); hi[0] = fmaxf(hi[0], b.x);
+                lo[1] = fminf(lo[1], b.y); hi[1] = fmaxf(hi[1], b.y);
+                lo[2] = fminf(lo[2], b.z); hi[2] = fmaxf(hi[2], b.z);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    __syncthreads();
+    if (tid < 3) {
+        float l = inf, h = -inf;
+        for (int w = 0; w < 8; ++w) { l = fminf(l, red[tid][w]); h = fmaxf(h, red[3 + tid][w]); }
+        if (!(l <= h)) { l = 0.0f; h = 0.0f; }                  // no finite vertex in this tile
+        box[tid] = l; box[3 + tid] = h;
+    }
+    __syncthreads();
+    Q16Hdr hd;
+    float lo_p[3], inv_p[3];
+    const int ax[3] = {axis_a, axis_b, axis_c};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float l = box[ax[k]], h = box[3 + ax[k]];
+        // a degenerate extent (all vertices on a plane normal to this axis) still gets a fine grid, so
+        // that the axis keeps pruning: steps of about 2^-20 of the coordinate magnitude
+        float ext = __fsub_rn(h, l);
+        ext = fmaxf(ext, fmaxf(fmaxf(fabsf(l), fabsf(h)) * 1.0e-6f, 1.0e-30f));
+        lo_p[k] = l;
+        inv_p[k] = __fdiv_rn(Q16_LEVELS, ext);
+    }
+    hd.lo_a = lo_p[0]; hd.lo_b = lo_p[1]; hd.lo_c = lo_p[2];
+    hd.inv_a = inv_p[0]; hd.inv_b = inv_p[1]; hd.inv_c = inv_p[2];
+    hd.cen_a = 0.5f * box[axis_a] + 0.5f * box[3 + axis_a];
+    hd.cen_b = 0.5f * box[axis_b] + 0.5f * box[3 + axis_b];
+    float* et = etiles + t * CYL_TILE_FLOATS;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = k * 256 + tid;
+        const float p[3] = {axis_of(x[k], y[k], z[k], axis_a), axis_of(x[k], y[k], z[k], axis_b),
+                            axis_of(x[k], y[k], z[k], axis_c)};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            unsigned short u = 65535;
+            if (fin[k]) {
+                // exact product of two floats in double; |u - (p - lo) inv| <= 0.5 (+ 1e-11)
+                double tq = ((double)p[a] - (double)lo_p[a]) * (double)inv_p[a];
+                tq = floor(tq + 0.5);
+                tq = tq < 0.0 ? 0.0 : (tq > (double)Q16_LEVELS ? (double)Q16_LEVELS : tq);
+                u = (unsigned short)tq;
+            }
+            us[a][i] = u;
+        }
+        et[i] = x[k]; et[NN_TILE + i] = y[k]; et[2 * NN_TILE + i] = z[k];
+        et[3 * NN_TILE + i] = __uint_as_float(oi[k]);
+    }
+    __syncthreads();
+    uint32_t* qt = qtiles + t * Q16_TILE_WORDS;
+    for (int w = tid; w < 3 * Q16_PLANE_WORDS; w += 256) {
+        const int a = w / Q16_PLANE_WORDS, i = w % Q16_PLANE_WORDS;
+        qt[w] = (uint32_t)us[a][2 * i] | ((uint32_t)us[a][2 * i + 1] << 16);
+    }
+    if (tid == 0) *reinterpret_cast<Q16Hdr*>(qt + 3 * Q16_PLANE_WORDS) = hd;
+}
+
+// per (query, tile, axis): the packed (-lo, -lo) addend and the packed width (W, W); W = 0 means the
+// query's interval misses the tile's range altogether ("never": min(x, 0) stays 0).  T < 0 marks a
+// padding slot (never).  NaN / inf inputs give the full range (the exact path then rejects them).
+__device__ __forceinline__ void q16_setup(float q, float T, float lo, float inv, uint32_t& nlo, uint32_t& wp)
+{
+    const float c = __fmul_rn(__fsub_rn(q, lo), inv);
+    const float r = __fmul_rn(T, inv);
+    // 2 steps: half a step of the stored u, the rest for floor/ceil; 2^-21 (|c| + r): the fp32
+    // rounding of c, r and of the two sums below
+    const float e = __fmaf_rn(4.8e-7f, __fadd_rn(fabsf(c), fabsf(r)), 2.0f);
+    const float lf = __fsub_rn(__fsub_rn(c, r), e), hf = __fadd_rn(__fadd_rn(c, r), e);
+    const bool never = (hf < 0.0f) || (lf > Q16_LEVELS) || (T < 0.0f);
+    const int li = __float2int_rd(fminf(fmaxf(lf, 0.0f), Q16_LEVELS));
+    const int hi = __float2int_ru(fminf(fmaxf(hf, 0.0f), Q16_LEVELS));
+    nlo = ((uint32_t)(65536 - li) & 0xFFFFu) * 0x10001u;
+    wp = never ? 0u : (uint32_t)(hi - li + 1) * 0x10001u;
+}
+
+__device__ __forceinline__ float q16_radius(float best)
+{
+    // sqrtf is correctly rounded; 1.000001 covers S4's own roundings (see the header comment)
+    return __fmul_rn(sqrtf(best), 1.000001f);
+}
+
+// Slow path (out of line): one query against one chunk of n_words * 2 vertices.
+//   tile : the shared-memory tile (planes a | b | c, header)      w0 : first word of the chunk
+//   ex   : the same chunk of the exact tile (global: x | y | z | original index planes)
+// `bound` is the squared pruning radius (<= the S4 distance of bkey's vertex).
+__device__ __noinline__ unsigned long long q16_recheck(const uint32_t* tile, int w0, int n_words,
+                                                       const float* __restrict__ ex, float qa, float qb,
+                                                       float qc, int axes, uint32_t index_offset,
+                                                       unsigned long long bkey, float bound)
+{
+    const float inf = __int_as_float(0x7f800000);
+    const Q16Hdr hd = *reinterpret_cast<const Q16Hdr*>(tile + 3 * Q16_PLANE_WORDS);
+    const int axis_a = axes & 3, axis_b = (axes >> 2) & 3;
+    const float ox = axis_a == 0 ? qa : (axis_b == 0 ? qb : qc);
+    const float oy = axis_a == 1 ? qa : (axis_b == 1 ? qb : qc);
+    const float oz = axis_a == 2 ? qa : (axis_b == 2 ? qb : qc);
+    uint32_t na, wa, nb, wb, nc, wc;
+    float T = q16_radius(bound);
+    q16_setup(qa, T, hd.lo_a, hd.inv_a, na, wa);
+    q16_setup(qb, T, hd.lo_b, hd.inv_b, nb, wb);
+    q16_setup(qc, T, hd.lo_c, hd.inv_c, nc, wc);
+    if (wa == 0u || wb == 0u || wc == 0u) return bkey;
+    const uint32_t* pa = tile + w0;
+    const uint32_t* pb = pa + Q16_PLANE_WORDS;
+    const uint32_t* pc = pb + Q16_PLANE_WORDS;
+    // chunk-level test on the two other axes first (the caller's slab axis passed already, but
+    // which one it was is not known here; three short loops cost less than the per-vertex pass)
+    {
+        uint32_t ma = wa, mb = wb, mc = wc;
+        for (int w = 0; w < n_words; ++w) {
+            ma = __viaddmin_u16x2(pa[w], na, ma);
+            mb = __viaddmin_u16x2(pb[w], nb, mb);
+            mc = __viaddmin_u16x2(pc[w], nc, mc);
+        }
+        if (ma == wa || mb == wb || mc == wc) return bkey;
+    }
+    uint32_t fa = ~wa, fb = ~wb, fc = ~wc;          // per half: 0xFFFF - W
+    for (int w = 0; w < n_words; ++w) {
+        // per half: e in [0, W], e < W iff inside; e + (0xFFFF - W) < 0xFFFF iff inside (no carry)
+        const uint32_t ea = __viaddmin_u16x2(pa[w], na, wa) + fa;
+        const uint32_t eb = __viaddmin_u16x2(pb[w], nb, wb) + fb;
+        const uint32_t ec = __viaddmin_u16x2(pc[w], nc, wc) + fc;
+        const uint32_t f = __vimax3_u16x2(ea, eb, ec);
+        if (f == 0xFFFFFFFFu) continue;             // neither vertex of the word is inside the box
+        bool improved = false;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (((f >> (16 * half)) & 0xFFFFu) == 0xFFFFu) continue;
+            const int i = 2 * w + half;                          // index inside the chunk
+            const float d = s4_d2(ox, oy, oz, ex[i], ex[NN_TILE + i], ex[2 * NN_TILE + i]);
+            if (d < inf) {
+                const unsigned long long k =
+                    ((unsigned long long)__float_as_uint(d) << 32) |
+                    (unsigned long long)(index_offset + __float_as_uint(ex[3 * NN_TILE + i]));
+                if (k < bkey) { bkey = k; improved = improved || (d < bound); }
+            }
+        }
+        if (improved) {                             // tighter box for the rest of the chunk
+            bound = fminf(bound, key_d2(bkey));
+            T = q16_radius(bound);
+            q16_setup(qa, T, hd.lo_a, hd.inv_a, na, wa);
+            q16_setup(qb, T, hd.lo_b, hd.inv_b, nb, wb);
+            q16_setup(qc, T, hd.lo_c, hd.inv_c, nc, wc);
+            if (wa == 0u || wb == 0u || wc == 0u) return bkey;
+            fa = ~wa; fb = ~wb; fc = ~wc;
+        }
+    }
+    return bkey;
+}
+
+// grid.x = query blocks of NN_THREADS * R slots, grid.y = base ranges of tiles_per_cta tiles.
+// Dynamic shared memory: STAGES * Q16_TILE_BYTES + 2 * STAGES * 8 (full / empty mbarriers).
+// `bound` (nullable): per-slot squared pruning radius from another source than the seed (the global
+// winner of the previous pass moved by the query's displacement, when the base is sharded).
+template <int R, int STAGES, int CH>
+__global__ void __launch_bounds__(NN_THREADS)
+k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict__ etiles, int axes,
+                    int n_tiles, int tiles_per_cta, const float* __restrict__ qx,
+                    const float* __restrict__ qy, const float* __restrict__ qz, long long n_queries,
+                    unsigned long long* __restrict__ keys, const float* __restrict__ bound,
+                    uint32_t index_offset, const int* __restrict__ stop_flag)
+{
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw);
+    constexpr int TILE_STRIDE = (Q16_TILE_BYTES + 127) / 128 * 128;      // 6272: keeps every slot 128-B aligned
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE_STRIDE);
+    uint64_t* empty = full + STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int t0 = blockIdx.y * tiles_per_cta;
+    const int t1 = min(n_tiles, t0 + tiles_per_cta);
+    const int my_tiles = t1 - t0;
+    if (my_tiles <= 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Q16_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < STAGES && s < my_tiles; ++s) {
+            mbar_expect_tx(&full[s], Q16_TILE_BYTES);
+            tma_load_1d(smem_raw + (size_t)s * TILE_STRIDE, qtiles + (size_t)(t0 + s) * Q16_TILE_WORDS,
+                        Q16_TILE_BYTES, &full[s]);
+        }
+    }
+
+    const int axis_a = axes & 3, axis_b = (axes >> 2) & 3, axis_c = (axes >> 4) & 3;
+    const long long q0 = (long long)blockIdx.x * (NN_THREADS * R) + tid;
+    float qa[R], qb[R], qc[R], bnd[R];
+    unsigned long long bkey[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const long long p = q0 + (long long)r * NN_THREADS;
+        const bool ok = p < n_queries;
+        const float x = ok ? qx[p] : 0.0f, y = ok ? qy[p] : 0.0f, z = ok ? qz[p] : 0.0f;
+        qa[r] = axis_of(x, y, z, axis_a); qb[r] = axis_of(x, y, z, axis_b); qc[r] = axis_of(x, y, z, axis_c);
+        bkey[r] = KEY_NONE;
+        // keys[p] of a seeded pass names a real vertex of this shard with its exact S4 distance
+        // under the current pose (K1 re-evaluated it; other CTAs can only have lowered it)
+        if (ok) bkey[r] = *reinterpret_cast<const volatile unsigned long long*>(&keys[p]);
+        bnd[r] = key_d2(bkey[r]);
+        if (ok && bound != nullptr) bnd[r] = fminf(bnd[r], bound[p]);
+        if (!ok) bnd[r] = -1.0f;                     // padding slot: q16_setup answers "never"
+    }
+
+    for (int it = 0; it < my_tiles; ++it) {
+        const int slot = it % STAGES;
+        mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
+        const uint32_t* tile = reinterpret_cast<const uint32_t*>(smem_raw + (size_t)slot * TILE_STRIDE);
+        const Q16Hdr hd = *reinterpret_cast<const Q16Hdr*>(tile + 3 * Q16_PLANE_WORDS);
+        // slab axis of this (warp, tile): the one along which most lanes are farther from the tile centre
+        const bool use_b = __popc(__ballot_sync(0xffffffffu, fabsf(qb[0] - hd.cen_b) > fabsf(qa[0] - hd.cen_a))) > 16;
+        const float lo_s = use_b ? hd.lo_b : hd.lo_a, inv_s = use_b ? hd.inv_b : hd.inv_a;
+        uint32_t nlo[R], wp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            q16_setup(use_b ? qb[r] : qa[r], bnd[r] < 0.0f ? -1.0f : q16_radius(bnd[r]), lo_s, inv_s, nlo[r], wp[r]);
+        const uint4* plane = reinterpret_cast<const uint4*>(tile + (use_b ? Q16_PLANE_WORDS : 0));
+#pragma unroll 1
+        for (int c = 0; c < NN_TILE / CH; ++c) {
+            uint32_t acc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = wp[r];
+#pragma unroll
+            for (int g = 0; g < CH / 8; ++g) {
+                const uint4 v = plane[c * (CH / 8) + g];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    acc[r] = __viaddmin_u16x2(v.x, nlo[r], acc[r]);
+                    acc[r] = __viaddmin_u16x2(v.y, nlo[r], acc[r]);
+                    acc[r] = __viaddmin_u16x2(v.z, nlo[r], acc[r]);
+                    acc[r] = __viaddmin_u16x2(v.w, nlo[r], acc[r]);
+                }
+            }
+            bool trig = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) trig = trig || (acc[r] != wp[r]);
+            if (trig) {
+                const float* ex = etiles + (size_t)(t0 + it) * CYL_TILE_FLOATS + c * CH;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (acc[r] == wp[r]) continue;
+                    const unsigned long long k = q16_recheck(tile, c * (CH / 2), CH / 2, ex, qa[r], qb[r], qc[r],
+                                                             axes, index_offset, bkey[r], bnd[r]);
+                    if (k != bkey[r]) {
+                        bkey[r] = k;
+                        const float d = key_d2(k);
+                        if (d < bnd[r]) {
+                            bnd[r] = d;
+                            q16_setup(use_b ? qb[r] : qa[r], q16_radius(d), lo_s, inv_s, nlo[r], wp[r]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);                   // this warp is done with the slot
+        if (tid == 0 && it >= 1 && it - 1 + STAGES < my_tiles) {    // late refill of the previous slot
+            const int j = it - 1, js = j % STAGES;
+            mbar_wait(&empty[js], (uint32_t)((j / STAGES) & 1));
+            mbar_expect_tx(&full[js], Q16_TILE_BYTES);
+            tma_load_1d(smem_raw + (size_t)js * TILE_STRIDE, qtiles + (size_t)(t0 + j + STAGES) * Q16_TILE_WORDS,
+                        Q16_TILE_BYTES, &full[js]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const long long p = q0 + (long long)r * NN_THREADS;
+        if (p < n_queries && bkey[r] != KEY_NONE) atomicMin(&keys[p], bkey[r]);
+    }
+}
+
+}  // namespace icp

@@ -94,7 +94,7 @@ def test_nn_vlist_stride_and_matrices():
         assert np.array_equal(d2.view(np.uint32), res["d2"].view(np.uint32))
 
 
-@pytest.mark.parametrize("variant", [20, 21, 30, 33, 35, 36, 40, 43])
+@pytest.mark.parametrize("variant", [20, 21, 30, 33, 35, 36, 40, 43, 44, 45, 50, 51, 54, 57])
 @pytest.mark.parametrize("case", ["surface", "far_outliers", "duplicates", "collinear", "volume", "lattice",
                                   "far_from_origin", "sorted_base"])
 def test_filter_kernel_matches_oracle(case, variant):
@@ -459,7 +459,7 @@ def test_tree_modes_keep_slot_order_and_seeds_across_same_shape_uploads(mode):
         assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
 
 
-@pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36, 40, 41, 42])
+@pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36, 40, 41, 42, 44, 45, 50, 51, 52, 53, 54, 55, 56, 57])
 def test_bruteforce_seeded_passes_stay_exact(variant):
     """From the second pass on the brute-force filter kernel starts its running minimum from the
     previous winner re-evaluated under the new pose.  Every pass must still return the oracle's
