@@ -800,6 +800,7 @@ struct icp_handle {
     int* d_vlist = nullptr;
     long long vlist_capacity = 0, n_vlist = 0;
     bool has_vlist = false, have_moving = false, have_matrices = false;
+    std::vector<int32_t> h_vlist;         // host copy of the uploaded vertex list (to recognise a repeated upload)
     // queries
     float* d_q = nullptr;                 // 3 planes of q_capacity
     unsigned long long* d_keys = nullptr;
@@ -908,7 +909,7 @@ bool uses_slots(const icp_handle* h)
 {
     if (h->prm.nn_mode != ICP_NN_BRUTEFORCE) return true;
     const int v = h->prm.nn_variant;
-    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36) || slab_variant(v) || (v >= 50 && v <= 58);
+    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36) || slab_variant(v) || (v >= 50 && v <= 69);
 }
 
 long long query_count(const icp_handle* h)
@@ -1258,10 +1259,10 @@ int build_q16(icp_handle* h, int want_order)
     return ICP_OK;
 }
 
-template <int R, int STAGES, int CH>
+template <int R, int STAGES, int CH, int MIX, int MINB = 1>
 int launch_nn_q16_t(icp_handle* h, long long n_q)
 {
-    auto kern = k_nn_bruteforce_q16<R, STAGES, CH>;
+    auto kern = k_nn_bruteforce_q16<R, STAGES, CH, MIX, MINB>;
     const size_t smem = (size_t)STAGES * ((Q16_TILE_BYTES + 127) / 128 * 128) + 2 * STAGES * sizeof(uint64_t);
     { int rc_ = configure_smem(h, kern, smem); if (rc_) return rc_; }
     const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
@@ -1285,7 +1286,7 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
     return ICP_OK;
 }
 
-bool q16_variant(int v) { return v >= 50 && v <= 58; }   // 58 = 50 without the global pruning bound (A/B)
+bool q16_variant(int v) { return v >= 50 && v <= 69; }   // 58 = 62 without the global pruning bound (A/B)
 
 int launch_nn(icp_handle* h, long long n_q)
 {
@@ -1293,11 +1294,11 @@ int launch_nn(icp_handle* h, long long n_q)
     int variant = h->prm.nn_variant;
     if (q16_variant(variant) && !h->bf_warm_active) variant = 0;       // the q16 kernel needs a seed: cold pass below
     if (variant == 0) {
-        if (h->bf_warm_active && h->n_tiles >= 16) variant = 50;       // seeded: 16-bit slab kernel
+        if (h->bf_warm_active && h->n_tiles >= 16) variant = 62;       // seeded: 16-bit slab kernel
         else variant = h->n_tiles >= 256 ? 20 : 2;                     // cold: filter / direct kernel
     }
     if (q16_variant(variant)) {
-        int rc = build_q16(h, (variant == 54 || variant == 55) ? 1 : 0);
+        int rc = build_q16(h, (variant == 54 || variant == 55 || variant == 66) ? 1 : 0);
         if (rc) return rc;
     }
     if (variant >= 20 && variant <= 29) {
@@ -1314,12 +1315,25 @@ int launch_nn(icp_handle* h, long long n_q)
     }
     ProfScope ps(h, 0);
     switch (variant) {
-        case 50: case 54: case 58: return launch_nn_q16_t<4, 4, 64>(h, n_q);
-        case 51: case 55: return launch_nn_q16_t<8, 4, 64>(h, n_q);
-        case 52: return launch_nn_q16_t<4, 4, 128>(h, n_q);
-        case 53: return launch_nn_q16_t<8, 4, 128>(h, n_q);
-        case 56: return launch_nn_q16_t<2, 4, 64>(h, n_q);
-        case 57: return launch_nn_q16_t<4, 4, 32>(h, n_q);
+        // q16, alu-only loop (VIADDMNMX): 50 = 4 queries/thread, 64-vertex chunks; 51 = 8 queries; 52, 53 = 128-vertex
+        // chunks; 54, 55 = 50, 51 with Morton order inside a tile; 56 = 2 queries; 57 = 32-vertex chunks
+        case 50: case 54: return launch_nn_q16_t<4, 4, 64, 0>(h, n_q);
+        case 51: case 55: return launch_nn_q16_t<8, 4, 64, 0>(h, n_q);
+        case 52: return launch_nn_q16_t<4, 4, 128, 0>(h, n_q);
+        case 53: return launch_nn_q16_t<8, 4, 128, 0>(h, n_q);
+        case 56: return launch_nn_q16_t<2, 4, 64, 0>(h, n_q);
+        case 57: return launch_nn_q16_t<4, 4, 32, 0>(h, n_q);
+        // q16, split loop (IMAD adds on the fma pipe + VIMNMX3 on the alu pipe): 60..65 blockings, 66 = 62 with
+        // Morton order inside a tile, 58 = 62 without the global pruning bound
+        case 60: return launch_nn_q16_t<4, 4, 64, 1>(h, n_q);
+        case 61: return launch_nn_q16_t<8, 4, 64, 1>(h, n_q);
+        case 62: case 66: case 58: return launch_nn_q16_t<4, 4, 128, 1>(h, n_q);
+        case 63: return launch_nn_q16_t<8, 4, 128, 1>(h, n_q);
+        case 64: return launch_nn_q16_t<4, 4, 256, 1>(h, n_q);
+        case 65: return launch_nn_q16_t<2, 4, 128, 1>(h, n_q);
+        case 67: return launch_nn_q16_t<6, 4, 128, 1>(h, n_q);
+        case 68: return launch_nn_q16_t<4, 4, 128, 1, 3>(h, n_q);      // 62 capped at 85 registers (3 CTAs per SM)
+        case 69: return launch_nn_q16_t<4, 4, 128, 1, 4>(h, n_q);      // 62 capped at 64 registers (4 CTAs per SM)
         case 40: return launch_nn_slab_t<4, 3, 32>(h, n_q);
         case 41: return launch_nn_slab_t<8, 3, 32>(h, n_q);
         case 42: return launch_nn_slab_t<4, 3, 64>(h, n_q);
@@ -1772,6 +1786,7 @@ int enqueue_iteration(icp_handle* h, long long n_q)
 int ensure_stats(icp_handle* h, int n)
 {
     if (n <= h->stats_capacity) return ICP_OK;
+    n = std::max(n, std::max(64, 2 * h->stats_capacity));      // geometric: a step()-per-tick caller reallocates O(log) times
     // keep what is there (n_iter indexes into it)
     icp_iter_stats* nw = nullptr;
     CUDA_TRY(h, cudaMalloc((void**)&nw, (size_t)n * sizeof(icp_iter_stats)));
@@ -1801,6 +1816,33 @@ int device_error(icp_handle* h, const DevState& st)
     if (st.error == ICP_ERR_SINGULAR)
         return fail(h, ICP_ERR_SINGULAR, "Matrix.invert(ed): matrix does not have an inverse");
     if (st.error) return fail(h, st.error, "device-side error %d", st.error);
+    return ICP_OK;
+}
+
+// The device-side `converged` flag is the stop flag of icp_run's enqueued iterations: every kernel
+// returns early on it.  icp_nn / icp_make_pairs are stand-alone queries and must not be silenced by a
+// run that converged earlier on this handle: they lift the latch for their own launches and put it
+// back afterwards (the convergence state of the run is untouched).
+int suspend_stop(icp_handle* h, int* saved)
+{
+    DevState st;
+    int rc = read_state(h, &st);
+    if (rc) return rc;
+    *saved = (st.converged && !st.error) ? 1 : 0;
+    if (*saved) {
+        const int zero = 0;
+        CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, converged), &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return ICP_OK;
+}
+
+int restore_stop(icp_handle* h, int saved)
+{
+    if (!saved) return ICP_OK;
+    const int one = 1;
+    CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, converged), &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return ICP_OK;
 }
 
@@ -2022,41 +2064,51 @@ int icp_set_moving(icp_handle* h, const float* xyz, int64_t n_vertices, const in
     if (!h) return ICP_ERR_BAD_ARG;
     if (n_vertices < 0 || (n_vertices > 0 && !xyz) || n_vlist < 0 || (vlist == nullptr && n_vlist != 0))
         return fail(h, ICP_ERR_BAD_ARG, "icp_set_moving: bad arguments");
+    // validate everything before any handle state changes: a rejected call leaves the handle as it was
+    if (vlist)
+        for (int64_t i = 0; i < n_vlist; ++i)
+            if (vlist[i] < 0 || vlist[i] >= n_vertices)
+                return fail(h, ICP_ERR_BAD_ARG, "icp_set_moving: vlist[%lld] = %d out of range", (long long)i, vlist[i]);
     CUDA_TRY(h, cudaSetDevice(h->prm.device));
     int rc = ensure(h, h->d_mov, h->mov_capacity, n_vertices * 3);
-    if (rc) return rc;
+    if (rc) { h->have_moving = false; return rc; }
+    if (vlist) {
+        rc = ensure(h, h->d_vlist, h->vlist_capacity, n_vlist);
+        if (rc) { h->have_moving = false; return rc; }
+    }
+    // Same vertex count and the same vertex list: this is normally the same mesh again (the operator
+    // and the function surface re-upload per call), so the Morton slot order and the previous winners
+    // are kept -- any order and any real base vertex / triangle as seed give the exact result, a stale
+    // one only costs speed -- and only the slot-ordered copy of the coordinates is refreshed.
+    const bool same_vlist = (vlist != nullptr) == h->has_vlist &&
+                            (!vlist || ((int64_t)h->h_vlist.size() == n_vlist &&
+                                        (n_vlist == 0 || memcmp(h->h_vlist.data(), vlist, (size_t)n_vlist * sizeof(int32_t)) == 0)));
+    const bool same_shape = h->have_moving && h->order_valid && n_vertices == h->n_vertices && same_vlist;
+    h->have_moving = false;                          // until every copy below has been queued
     if (n_vertices > 0)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_mov, xyz, (size_t)n_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    // Same vertex count and no mask: this is normally the same mesh again (the operator re-uploads per
-    // call), so the Morton slot order and the previous winners are kept -- any order and any real base
-    // vertex / triangle as seed give the exact result, a stale one only costs speed -- and only the
-    // slot-ordered copy of the coordinates is refreshed.
-    const bool same_shape = h->have_moving && h->order_valid && n_vertices == h->n_vertices && !vlist && !h->has_vlist;
+    if (vlist && n_vlist > 0 && !same_vlist)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_vlist, vlist, (size_t)n_vlist * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    // moments are accumulated about the first vertex of the (replicated) moving array, so that
+    // every rank of a query-sharded run uses the same reference point
+    double shift[3] = {0, 0, 0};
+    if (n_vertices > 0)
+        for (int k = 0; k < 3; ++k) shift[k] = xyz[k];
+    CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, shift), shift, sizeof(shift), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (!same_vlist) {
+        if (vlist) h->h_vlist.assign(vlist, vlist + n_vlist);
+        else h->h_vlist.clear();
+    }
     h->n_vertices = n_vertices;
+    h->has_vlist = vlist != nullptr;
+    h->n_vlist = n_vlist;
     if (same_shape) {
         h->slots_stale = true;
     } else {
         h->order_valid = false;
         h->warm_valid = false;
     }
-    h->has_vlist = vlist != nullptr;
-    h->n_vlist = n_vlist;
-    // moments are accumulated about the first vertex of the (replicated) moving array, so that
-    // every rank of a query-sharded run uses the same reference point
-    double shift[3] = {0, 0, 0};
-    if (n_vertices > 0)
-        for (int k = 0; k < 3; ++k) shift[k] = xyz[k];
-    if (vlist) {
-        for (int64_t i = 0; i < n_vlist; ++i)
-            if (vlist[i] < 0 || vlist[i] >= n_vertices)
-                return fail(h, ICP_ERR_BAD_ARG, "icp_set_moving: vlist[%lld] = %d out of range", (long long)i, vlist[i]);
-        rc = ensure(h, h->d_vlist, h->vlist_capacity, n_vlist);
-        if (rc) return rc;
-        if (n_vlist > 0)
-            CUDA_TRY(h, cudaMemcpyAsync(h->d_vlist, vlist, (size_t)n_vlist * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    }
-    CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_state + offsetof(DevState, shift), shift, sizeof(shift), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_moving = true;
     return ICP_OK;
 }
@@ -2111,9 +2163,12 @@ int icp_nn(icp_handle* h, int32_t* idx, float* d2)
     if (rc) return rc;
     CUDA_TRY(h, cudaSetDevice(h->prm.device));
     const long long n_q = query_count(h);
+    int latched = 0;
+    rc = suspend_stop(h, &latched);
+    if (rc) return rc;
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     rc = enqueue_nn(h, n_q);
-    if (rc) return rc;
+    if (rc) { restore_stop(h, latched); return rc; }
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     if (n_q > 0 && (idx || d2)) {
         int* d_idx = nullptr; float* d_d2 = nullptr;
@@ -2135,8 +2190,11 @@ int icp_nn(icp_handle* h, int32_t* idx, float* d2)
     if (rc) return rc;
     rc = device_error(h, st);
     if (rc) { clear_device_error(h); return rc; }
-    return ICP_OK;
+    return restore_stop(h, latched);
 }
+
+static int make_pairs_body(icp_handle* h, int calc_stats, double* A, double* B, int64_t capacity,
+                           int64_t* pairs_out, double d_stats[2]);
 
 int icp_make_pairs(icp_handle* h, int calc_stats, double* A, double* B, int64_t capacity,
                    int64_t* pairs_out, double d_stats[2])
@@ -2147,6 +2205,18 @@ int icp_make_pairs(icp_handle* h, int calc_stats, double* A, double* B, int64_t 
         return fail(h, ICP_ERR_STATE, "icp_make_pairs materialises pairs on one GPU; use icp_step/icp_run with sharded bases");
     if (!pairs_out) return fail(h, ICP_ERR_BAD_ARG, "icp_make_pairs: pairs_out is null");
     CUDA_TRY(h, cudaSetDevice(h->prm.device));
+    int latched = 0;
+    rc = suspend_stop(h, &latched);
+    if (rc) return rc;
+    rc = make_pairs_body(h, calc_stats, A, B, capacity, pairs_out, d_stats);
+    const int rc2 = restore_stop(h, latched);
+    return rc ? rc : rc2;
+}
+
+static int make_pairs_body(icp_handle* h, int calc_stats, double* A, double* B, int64_t capacity,
+                           int64_t* pairs_out, double d_stats[2])
+{
+    int rc;
     const long long n_q = query_count(h);
     rc = enqueue_nn(h, n_q);
     if (rc) return rc;

@@ -153,6 +153,10 @@ k_build_q16_tiles(const float4* __restrict__ base4, const uint32_t* __restrict__
 // per (query, tile, axis): the packed (-lo, -lo) addend and the packed width (W, W); W = 0 means the
 // query's interval misses the tile's range altogether ("never": min(x, 0) stays 0).  T < 0 marks a
 // padding slot (never).  NaN / inf inputs give the full range (the exact path then rejects them).
+// CARRY: the hot loop adds the packed addend with a plain 32-bit add (IMAD on the fma pipe), so a
+// carry out of the low half can raise the high half by one: the width grows by one step to keep the
+// test conservative (no carry can occur when lo == 0, where the addend is 0).
+template <bool CARRY = false>
 __device__ __forceinline__ void q16_setup(float q, float T, float lo, float inv, uint32_t& nlo, uint32_t& wp)
 {
     const float c = __fmul_rn(__fsub_rn(q, lo), inv);
@@ -165,7 +169,15 @@ __device__ __forceinline__ void q16_setup(float q, float T, float lo, float inv,
     const int li = __float2int_rd(fminf(fmaxf(lf, 0.0f), Q16_LEVELS));
     const int hi = __float2int_ru(fminf(fmaxf(hf, 0.0f), Q16_LEVELS));
     nlo = ((uint32_t)(65536 - li) & 0xFFFFu) * 0x10001u;
-    wp = never ? 0u : (uint32_t)(hi - li + 1) * 0x10001u;
+    wp = never ? 0u : (uint32_t)(hi - li + 1 + ((CARRY && li > 0) ? 1 : 0)) * 0x10001u;
+}
+
+// 32-bit add on the fma pipe (IMAD.IADD), leaving the alu pipe to the min instructions
+__device__ __forceinline__ uint32_t iadd_fma(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
 }
 
 __device__ __forceinline__ float q16_radius(float best)
@@ -247,8 +259,11 @@ __device__ __noinline__ unsigned long long q16_recheck(const uint32_t* tile, int
 // Dynamic shared memory: STAGES * Q16_TILE_BYTES + 2 * STAGES * 8 (full / empty mbarriers).
 // `bound` (nullable): per-slot squared pruning radius from another source than the seed (the global
 // winner of the previous pass moved by the query's displacement, when the base is sharded).
-template <int R, int STAGES, int CH>
-__global__ void __launch_bounds__(NN_THREADS)
+// MIX = 0: one VIADDMNMX.U16x2 per word (2 vertices), alu pipe only: 2.0 cycles per warp instruction.
+// MIX = 1: two IMAD adds (fma pipe) + one VIMNMX3.U16x2 (alu pipe) per two words (4 vertices): the pipes
+//          overlap, 2.65 cycles per 4 vertices against 4.0 (tools/ubench/pipes3.cu).
+template <int R, int STAGES, int CH, int MIX, int MINB>
+__global__ void __launch_bounds__(NN_THREADS, MINB)
 k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict__ etiles, int axes,
                     int n_tiles, int tiles_per_cta, const float* __restrict__ qx,
                     const float* __restrict__ qy, const float* __restrict__ qz, long long n_queries,
@@ -257,7 +272,6 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
 {
     if (stop_flag != nullptr && *stop_flag != 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw);
     constexpr int TILE_STRIDE = (Q16_TILE_BYTES + 127) / 128 * 128;      // 6272: keeps every slot 128-B aligned
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE_STRIDE);
     uint64_t* empty = full + STAGES;
@@ -284,7 +298,7 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
 
     const int axis_a = axes & 3, axis_b = (axes >> 2) & 3, axis_c = (axes >> 4) & 3;
     const long long q0 = (long long)blockIdx.x * (NN_THREADS * R) + tid;
-    float qa[R], qb[R], qc[R], bnd[R];
+    float qa[R], qb[R], qc[R], bnd[R], rad[R];      // bnd: squared pruning radius, rad: its root (< 0: padding slot)
     unsigned long long bkey[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -298,7 +312,7 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
         if (ok) bkey[r] = *reinterpret_cast<const volatile unsigned long long*>(&keys[p]);
         bnd[r] = key_d2(bkey[r]);
         if (ok && bound != nullptr) bnd[r] = fminf(bnd[r], bound[p]);
-        if (!ok) bnd[r] = -1.0f;                     // padding slot: q16_setup answers "never"
+        rad[r] = ok ? q16_radius(bnd[r]) : -1.0f;    // padding slot: q16_setup answers "never"
     }
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -312,7 +326,7 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
         uint32_t nlo[R], wp[R];
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            q16_setup(use_b ? qb[r] : qa[r], bnd[r] < 0.0f ? -1.0f : q16_radius(bnd[r]), lo_s, inv_s, nlo[r], wp[r]);
+            q16_setup<MIX == 1>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
         const uint4* plane = reinterpret_cast<const uint4*>(tile + (use_b ? Q16_PLANE_WORDS : 0));
 #pragma unroll 1
         for (int c = 0; c < NN_TILE / CH; ++c) {
@@ -324,10 +338,15 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
                 const uint4 v = plane[c * (CH / 8) + g];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    acc[r] = __viaddmin_u16x2(v.x, nlo[r], acc[r]);
-                    acc[r] = __viaddmin_u16x2(v.y, nlo[r], acc[r]);
-                    acc[r] = __viaddmin_u16x2(v.z, nlo[r], acc[r]);
-                    acc[r] = __viaddmin_u16x2(v.w, nlo[r], acc[r]);
+                    if (MIX == 0) {
+                        acc[r] = __viaddmin_u16x2(v.x, nlo[r], acc[r]);
+                        acc[r] = __viaddmin_u16x2(v.y, nlo[r], acc[r]);
+                        acc[r] = __viaddmin_u16x2(v.z, nlo[r], acc[r]);
+                        acc[r] = __viaddmin_u16x2(v.w, nlo[r], acc[r]);
+                    } else {
+                        acc[r] = __vimin3_u16x2(acc[r], iadd_fma(v.x, nlo[r]), iadd_fma(v.y, nlo[r]));
+                        acc[r] = __vimin3_u16x2(acc[r], iadd_fma(v.z, nlo[r]), iadd_fma(v.w, nlo[r]));
+                    }
                 }
             }
             bool trig = false;
@@ -345,7 +364,8 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
                         const float d = key_d2(k);
                         if (d < bnd[r]) {
                             bnd[r] = d;
-                            q16_setup(use_b ? qb[r] : qa[r], q16_radius(d), lo_s, inv_s, nlo[r], wp[r]);
+                            rad[r] = q16_radius(d);
+                            q16_setup<MIX == 1>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
                         }
                     }
                 }

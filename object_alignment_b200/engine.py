@@ -212,14 +212,18 @@ class IcpEngine:
         return idx, d2
 
     def make_pairs(self, calc_stats=False):
+        """(A, B, d_stats) of the reference's make_pairs (general.py:257-329).  ONE search: the output
+        arrays are sized for every query (row stride = capacity) and sliced to the K kept pairs."""
+        cap = max(self.query_count(), 1)
         k = C.c_int64()
-        self._check(self._lib.icp_make_pairs(self._h, 0, None, None, 0, C.byref(k), None))
-        K = k.value
-        A = np.zeros((3, K), dtype=np.float64)
-        B = np.zeros((3, K), dtype=np.float64)
+        A = np.empty((3, cap), dtype=np.float64)
+        B = np.empty((3, cap), dtype=np.float64)
         ds = np.zeros(2, dtype=np.float64)
         self._check(self._lib.icp_make_pairs(self._h, 1 if calc_stats else 0, A.ctypes.data,
-                                             B.ctypes.data, K, C.byref(k), ds.ctypes.data))
+                                             B.ctypes.data, cap, C.byref(k), ds.ctypes.data))
+        K = k.value
+        A = np.ascontiguousarray(A[:, :K])
+        B = np.ascontiguousarray(B[:, :K])
         return A, B, ([float(ds[0]), float(ds[1])] if calc_stats else None)
 
     def solve_pairs(self, v0, v1, scale=False):

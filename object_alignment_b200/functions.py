@@ -90,41 +90,59 @@ class VertexNN:
 
     def __init__(self, base_coords, **engine_kwargs):
         engine_kwargs.setdefault("nn_mode", DEFAULT_NN_MODE)
+        if engine_kwargs.get("world_size", 1) > 1:
+            # the O(log N) searches shard the QUERIES (base replicated); only brute force shards the base
+            engine_kwargs.setdefault("shard_mode", N.SHARD_BASE if engine_kwargs["nn_mode"] == N.NN_BRUTEFORCE
+                                     else N.SHARD_QUERIES)
         self.engine = IcpEngine(**engine_kwargs)
         base_coords = np.ascontiguousarray(base_coords, dtype=np.float32).reshape(-1, 3)
         self.n_base = base_coords.shape[0]
-        if self.engine.params.world_size > 1:
+        self._upload_base(base_coords)
+
+    def _upload_base(self, base_coords):
+        if self._base_is_sharded():
             self.engine.set_base_sharded(base_coords)
         else:
             self.engine.set_base(base_coords)
-        self._moving_key = None
+
+    def _base_is_sharded(self):
+        p = self.engine.params
+        return p.world_size > 1 and p.shard_mode == N.SHARD_BASE
+
+    def connect(self, dist=None):
+        """Collective (world_size > 1): build the NCCL communicator of this index's engine."""
+        from .dist import connect_engine
+        connect_engine(self.engine, dist)
 
     @classmethod
     def FromObject(cls, obj, depsgraph=None, **engine_kwargs):
         return cls(extract_coords(obj), **engine_kwargs)
 
     def invalidate(self):
-        """Forget the cached moving-object upload (call after editing the align mesh)."""
-        self._moving_key = None
+        """Kept for callers of the first version; the coordinates are re-read on every call now."""
 
-    # internal: upload moving vertices + vlist only when they changed
+    # internal: the reference reads vert.co on every call (general.py:284), so do we -- the C side keeps
+    # its Morton slot order and the previous winners when the vertex count and vlist are unchanged
     def _bind_moving(self, align_obj, vlist):
         vl = np.ascontiguousarray(vlist, dtype=np.int32)
-        verts = align_obj.data.vertices
-        key = (id(align_obj.data), len(verts), vl.shape[0], hash(vl.tobytes()))
-        if key != self._moving_key:
-            self.engine.set_moving(extract_coords(align_obj), vl)
-            self._moving_key = key
+        coords = extract_coords(align_obj)
+        p = self.engine.params
+        if p.world_size > 1 and p.shard_mode == N.SHARD_QUERIES:
+            self.engine.update_params(stride=self._stride)
+            self.engine.set_moving_sharded(coords, vl)
+        else:
+            self.engine.set_moving(coords, vl)
 
     def _bind(self, align_obj, base_obj, vlist, thresh=None, sample=0, **params):
-        self._bind_moving(align_obj, vlist)
-        self.engine.set_matrices(matrix_to_array(align_obj.matrix_world),
-                                 matrix_to_array(base_obj.matrix_world))
-        upd = dict(stride=int(sample) if sample and sample > 1 else 1)
+        self._stride = int(sample) if sample and sample > 1 else 1
+        upd = dict(stride=self._stride)
         if thresh is not None:
             upd["thresh"] = float(thresh)
         upd.update(params)
         self.engine.update_params(**upd)
+        self._bind_moving(align_obj, vlist)      # query-sharded engines fold the stride into their slice here
+        self.engine.set_matrices(matrix_to_array(align_obj.matrix_world),
+                                 matrix_to_array(base_obj.matrix_world))
 
     def close(self):
         self.engine.close()
@@ -137,16 +155,17 @@ class SurfaceNN(VertexNN):
 
     def __init__(self, base_coords, triangles, **engine_kwargs):
         engine_kwargs["nn_mode"] = N.NN_SURFACE
+        if engine_kwargs.get("world_size", 1) > 1:
+            engine_kwargs.setdefault("shard_mode", N.SHARD_QUERIES)
         self.engine = IcpEngine(**engine_kwargs)
         coords = np.ascontiguousarray(base_coords, dtype=np.float32).reshape(-1, 3)
         tris = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
         self.n_base = tris.shape[0]
         corners = np.ascontiguousarray(coords[tris].reshape(-1, 9))
-        if self.engine.params.world_size > 1:
+        if self._base_is_sharded():
             self.engine.set_base_triangles_sharded(corners)
         else:
             self.engine.set_base_triangles(corners)
-        self._moving_key = None
 
     @classmethod
     def FromObject(cls, obj, depsgraph=None, **engine_kwargs):
