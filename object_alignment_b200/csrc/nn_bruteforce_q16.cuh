@@ -29,9 +29,9 @@
 // interval is always inside the integer one (tests/test_filter_bounds.py restates it in numpy).
 //
 // A chunk that triggers for a query is re-tested per vertex with the 3-axis integer box (three
-// VIADDMNMX + one VIMNMX3.U16x2 per two vertices), and only vertices inside the box get the exact S4
-// metric from the exact tile in global memory -- so the 64-bit keys are bit-identical to the direct
-// kernel's, ties to the lowest ORIGINAL index.
+// VIADDMNMX + one VIMNMX3.U16x2 per two vertices) by the whole warp together, and only vertices inside
+// the box get the exact S4 metric from the exact tile in global memory -- so the 64-bit keys are
+// bit-identical to the direct kernel's, ties to the lowest ORIGINAL index.
 #pragma once
 #include "nn_bruteforce_slab.cuh"
 
@@ -186,73 +186,62 @@ __device__ __forceinline__ float q16_radius(float best)
     return __fmul_rn(sqrtf(best), 1.000001f);
 }
 
-// Slow path (out of line): one query against one chunk of n_words * 2 vertices.
+// Slow path, warp-cooperative: ALL 32 lanes re-check one (query, chunk) pair together.  The owner's
+// query is broadcast by the caller; every lane tests CH / 64 words (two vertices each) of the chunk
+// against the 3-axis integer box (three VIADDMNMX + one VIMNMX3.U16x2 per word), lanes whose vertices
+// fall inside evaluate the exact S4 metric on the exact tile in global memory, and the smallest 64-bit
+// key is reduced over the warp: ~100 warp instructions per triggered (query, chunk), whatever CH is.
 //   tile : the shared-memory tile (planes a | b | c, header)      w0 : first word of the chunk
 //   ex   : the same chunk of the exact tile (global: x | y | z | original index planes)
-// `bound` is the squared pruning radius (<= the S4 distance of bkey's vertex).
-__device__ __noinline__ unsigned long long q16_recheck(const uint32_t* tile, int w0, int n_words,
-                                                       const float* __restrict__ ex, float qa, float qb,
-                                                       float qc, int axes, uint32_t index_offset,
-                                                       unsigned long long bkey, float bound)
+//   T    : the query's pruning radius.   Returns the best key found in the chunk, or KEY_NONE.
+template <int CH>
+__device__ __forceinline__ unsigned long long q16_recheck_warp(const uint32_t* tile, const Q16Hdr& hd, int w0,
+                                                               const float* __restrict__ ex, float qa, float qb,
+                                                               float qc, float T, int axes, uint32_t index_offset,
+                                                               int lane)
 {
     const float inf = __int_as_float(0x7f800000);
-    const Q16Hdr hd = *reinterpret_cast<const Q16Hdr*>(tile + 3 * Q16_PLANE_WORDS);
     const int axis_a = axes & 3, axis_b = (axes >> 2) & 3;
     const float ox = axis_a == 0 ? qa : (axis_b == 0 ? qb : qc);
     const float oy = axis_a == 1 ? qa : (axis_b == 1 ? qb : qc);
     const float oz = axis_a == 2 ? qa : (axis_b == 2 ? qb : qc);
     uint32_t na, wa, nb, wb, nc, wc;
-    float T = q16_radius(bound);
     q16_setup(qa, T, hd.lo_a, hd.inv_a, na, wa);
     q16_setup(qb, T, hd.lo_b, hd.inv_b, nb, wb);
     q16_setup(qc, T, hd.lo_c, hd.inv_c, nc, wc);
-    if (wa == 0u || wb == 0u || wc == 0u) return bkey;
-    const uint32_t* pa = tile + w0;
-    const uint32_t* pb = pa + Q16_PLANE_WORDS;
-    const uint32_t* pc = pb + Q16_PLANE_WORDS;
-    // chunk-level test on the two other axes first (the caller's slab axis passed already, but
-    // which one it was is not known here; three short loops cost less than the per-vertex pass)
-    {
-        uint32_t ma = wa, mb = wb, mc = wc;
-        for (int w = 0; w < n_words; ++w) {
-            ma = __viaddmin_u16x2(pa[w], na, ma);
-            mb = __viaddmin_u16x2(pb[w], nb, mb);
-            mc = __viaddmin_u16x2(pc[w], nc, mc);
-        }
-        if (ma == wa || mb == wb || mc == wc) return bkey;
-    }
-    uint32_t fa = ~wa, fb = ~wb, fc = ~wc;          // per half: 0xFFFF - W
-    for (int w = 0; w < n_words; ++w) {
-        // per half: e in [0, W], e < W iff inside; e + (0xFFFF - W) < 0xFFFF iff inside (no carry)
-        const uint32_t ea = __viaddmin_u16x2(pa[w], na, wa) + fa;
-        const uint32_t eb = __viaddmin_u16x2(pb[w], nb, wb) + fb;
-        const uint32_t ec = __viaddmin_u16x2(pc[w], nc, wc) + fc;
-        const uint32_t f = __vimax3_u16x2(ea, eb, ec);
-        if (f == 0xFFFFFFFFu) continue;             // neither vertex of the word is inside the box
-        bool improved = false;
+    unsigned long long best = KEY_NONE;
+    if (wa != 0u && wb != 0u && wc != 0u) {          // warp-uniform: every lane holds the same query
+        const uint32_t fa = ~wa, fb = ~wb, fc = ~wc; // per half: 0xFFFF - W
+        constexpr int WPC = CH / 2;                  // words per chunk
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if (((f >> (16 * half)) & 0xFFFFu) == 0xFFFFu) continue;
-            const int i = 2 * w + half;                          // index inside the chunk
-            const float d = s4_d2(ox, oy, oz, ex[i], ex[NN_TILE + i], ex[2 * NN_TILE + i]);
-            if (d < inf) {
-                const unsigned long long k =
-                    ((unsigned long long)__float_as_uint(d) << 32) |
-                    (unsigned long long)(index_offset + __float_as_uint(ex[3 * NN_TILE + i]));
-                if (k < bkey) { bkey = k; improved = improved || (d < bound); }
+        for (int j = 0; j * 32 < WPC; ++j) {
+            const int wl = lane + 32 * j;
+            if (WPC % 32 != 0 && wl >= WPC) break;
+            const uint32_t* pw = tile + w0 + wl;
+            // per half: e in [0, W], e < W iff inside; e + (0xFFFF - W) < 0xFFFF iff inside (no carry)
+            const uint32_t ea = __viaddmin_u16x2(pw[0], na, wa) + fa;
+            const uint32_t eb = __viaddmin_u16x2(pw[Q16_PLANE_WORDS], nb, wb) + fb;
+            const uint32_t ec = __viaddmin_u16x2(pw[2 * Q16_PLANE_WORDS], nc, wc) + fc;
+            const uint32_t f = __vimax3_u16x2(ea, eb, ec);
+            if (f == 0xFFFFFFFFu) continue;          // neither vertex of the word is inside the box
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (((f >> (16 * half)) & 0xFFFFu) == 0xFFFFu) continue;
+                const int i = 2 * wl + half;         // index inside the chunk
+                const float d = s4_d2(ox, oy, oz, ex[i], ex[NN_TILE + i], ex[2 * NN_TILE + i]);
+                if (d < inf) {
+                    const unsigned long long k =
+                        ((unsigned long long)__float_as_uint(d) << 32) |
+                        (unsigned long long)(index_offset + __float_as_uint(ex[3 * NN_TILE + i]));
+                    best = k < best ? k : best;
+                }
             }
         }
-        if (improved) {                             // tighter box for the rest of the chunk
-            bound = fminf(bound, key_d2(bkey));
-            T = q16_radius(bound);
-            q16_setup(qa, T, hd.lo_a, hd.inv_a, na, wa);
-            q16_setup(qb, T, hd.lo_b, hd.inv_b, nb, wb);
-            q16_setup(qc, T, hd.lo_c, hd.inv_c, nc, wc);
-            if (wa == 0u || wb == 0u || wc == 0u) return bkey;
-            fa = ~wa; fb = ~wb; fc = ~wc;
-        }
     }
-    return bkey;
+    const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+    const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mhi << 32) | (unsigned long long)mlo;
 }
 
 // grid.x = query blocks of NN_THREADS * R slots, grid.y = base ranges of tiles_per_cta tiles.
@@ -352,20 +341,27 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
             bool trig = false;
 #pragma unroll
             for (int r = 0; r < R; ++r) trig = trig || (acc[r] != wp[r]);
-            if (trig) {
+            if (__any_sync(0xffffffffu, trig)) {
+                // all lanes serve the triggered (lane, query) pairs of this chunk one after the other
                 const float* ex = etiles + (size_t)(t0 + it) * CYL_TILE_FLOATS + c * CH;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (acc[r] == wp[r]) continue;
-                    const unsigned long long k = q16_recheck(tile, c * (CH / 2), CH / 2, ex, qa[r], qb[r], qc[r],
-                                                             axes, index_offset, bkey[r], bnd[r]);
-                    if (k != bkey[r]) {
-                        bkey[r] = k;
-                        const float d = key_d2(k);
-                        if (d < bnd[r]) {
-                            bnd[r] = d;
-                            rad[r] = q16_radius(d);
-                            q16_setup<MIX == 1>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
+                    unsigned todo = __ballot_sync(0xffffffffu, acc[r] != wp[r]);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const float sa = __shfl_sync(0xffffffffu, qa[r], src), sb = __shfl_sync(0xffffffffu, qb[r], src),
+                                    sc = __shfl_sync(0xffffffffu, qc[r], src), sT = __shfl_sync(0xffffffffu, rad[r], src);
+                        const unsigned long long k = q16_recheck_warp<CH>(tile, hd, c * (CH / 2), ex, sa, sb, sc, sT, axes,
+                                                                          index_offset, lane);
+                        if (lane == src && k < bkey[r]) {
+                            bkey[r] = k;
+                            const float d = key_d2(k);
+                            if (d < bnd[r]) {
+                                bnd[r] = d;
+                                rad[r] = q16_radius(d);
+                                q16_setup<MIX == 1>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
+                            }
                         }
                     }
                 }

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- import the UNMODIFIED reference under stub Blender modules.
 
-Works only where ``/root/reference`` exists (this container; NOT the GPU box).  Used by
+Runs the files under ``/root/reference`` (this container) or their staged byte-for-byte copies under
+``oracle/_ref`` (the GPU box; see ``oracle/stage_ref.py``).  Used by
 ``oracle/gen_golden.py`` to produce ``tests/golden/*.npz`` and by the CPU tests that pin
 ``oracle/icp_oracle.py`` against the live reference when it is present.
 
@@ -20,7 +21,18 @@ import warnings
 
 from . import mathutils_shim as ms
 
-REFERENCE_ROOT = os.environ.get("ICP_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """ICP_REFERENCE_ROOT, else the read-only checkout, else the staged copy (oracle/stage_ref.py)."""
+    env = os.environ.get("ICP_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")):
+        if os.path.isfile(os.path.join(cand, "functions", "general.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _PKG = "refpkg_object_alignment"
 
 
