@@ -74,7 +74,8 @@ typedef struct icp_params {
     int32_t nn_variant;      /* kernel variant for tuning / A-B runs; 0 = library default.  Every variant
                                 returns the same keys.  Brute force: 1-6 direct metric, 20-24 expansion
                                 filter, 30-36 cylinder filter, 40-45 slab filter (default for seeded
-                                passes: 42).  BVH: 10 per-thread walk, 11 packet walk without the fused
+                                passes until round 2), 50-57 / 60-69 16-bit quantised slab test (alu-only /
+                                split fma+alu loop; default for seeded passes: 62).  BVH: 10 per-thread walk, 11 packet walk without the fused
                                 epilogue.  Surface: 10 per-thread walk, 11 packet walk with eager
                                 triangle tests (default: deferred tests)                          */
     int32_t shard_mode;      /* icp_shard_mode when world_size > 1                               */
@@ -119,6 +120,12 @@ int  icp_set_base_triangles(icp_handle *h, const float *tri_xyz, int64_t n_local
  * means all vertices (icp_align.py:80).  Indices must be in [0, n_vertices). */
 int  icp_set_moving(icp_handle *h, const float *xyz, int64_t n_vertices, const int32_t *vlist,
                     int64_t n_vlist);
+/* Collective form for a multi-GPU run in which every rank holds the same host array (world_size > 1,
+ * after icp_comm_init; every rank must call it): each rank sends only its 1/world_size slice of the
+ * coordinates over its host link and the slices are exchanged with ncclAllGather over NVLink.  Same
+ * result as icp_set_moving on every rank. */
+int  icp_set_moving_collective(icp_handle *h, const float *xyz, int64_t n_vertices, const int32_t *vlist,
+                               int64_t n_vlist);
 /* align_obj.matrix_world and base_obj.matrix_world (general.py:262-263), fp32 row-major. */
 int  icp_set_matrices(icp_handle *h, const float mw_align[16], const float mw_base[16]);
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "icp_set_base": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "icp_set_base_triangles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "icp_set_moving": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "icp_set_moving_collective": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "icp_set_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "icp_comm_unique_id": (C.c_int, [C.c_void_p]),
     "icp_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -700,6 +700,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load(char* err, size_t n)
@@ -713,9 +714,10 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) {
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !AllGather || !CommDestroy || !GetErrorString) {
             snprintf(err, n, "libnccl is missing required symbols");
             lib = nullptr;
             return false;
@@ -1270,8 +1272,10 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
     if (occ < 1) occ = 1;
     const long long slots = (long long)h->sm_count * occ;
-    long long want_y = (8 * slots + qb - 1) / qb;
-    long long max_y = std::max<long long>(1, h->n_tiles / 8);
+    // ~24 waves (a CTA's duration varies with its slow-path work: ncu showed 13 % of the SM time idle in the
+    // tail at 8.8 waves), every CTA still streams >= 4 tiles
+    long long want_y = (24 * slots + qb - 1) / qb;
+    long long max_y = std::max<long long>(1, h->n_tiles / 4);
     long long gy = std::max<long long>(1, std::min(want_y, max_y));
     int tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy);
     gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta;
@@ -1317,23 +1321,26 @@ int launch_nn(icp_handle* h, long long n_q)
     switch (variant) {
         // q16, alu-only loop (VIADDMNMX): 50 = 4 queries/thread, 64-vertex chunks; 51 = 8 queries; 52, 53 = 128-vertex
         // chunks; 54, 55 = 50, 51 with Morton order inside a tile; 56 = 2 queries; 57 = 32-vertex chunks
-        case 50: case 54: return launch_nn_q16_t<4, 4, 64, 0>(h, n_q);
+        case 50: case 54: return launch_nn_q16_t<4, 4, 64, 0, 3>(h, n_q);
         case 51: case 55: return launch_nn_q16_t<8, 4, 64, 0>(h, n_q);
-        case 52: return launch_nn_q16_t<4, 4, 128, 0>(h, n_q);
+        case 52: return launch_nn_q16_t<4, 4, 128, 0, 3>(h, n_q);
         case 53: return launch_nn_q16_t<8, 4, 128, 0>(h, n_q);
-        case 56: return launch_nn_q16_t<2, 4, 64, 0>(h, n_q);
-        case 57: return launch_nn_q16_t<4, 4, 32, 0>(h, n_q);
-        // q16, split loop (IMAD adds on the fma pipe + VIMNMX3 on the alu pipe): 60..65 blockings, 66 = 62 with
-        // Morton order inside a tile, 58 = 62 without the global pruning bound
-        case 60: return launch_nn_q16_t<4, 4, 64, 1>(h, n_q);
-        case 61: return launch_nn_q16_t<8, 4, 64, 1>(h, n_q);
-        case 62: case 66: case 58: return launch_nn_q16_t<4, 4, 128, 1>(h, n_q);
-        case 63: return launch_nn_q16_t<8, 4, 128, 1>(h, n_q);
-        case 64: return launch_nn_q16_t<4, 4, 256, 1>(h, n_q);
-        case 65: return launch_nn_q16_t<2, 4, 128, 1>(h, n_q);
-        case 67: return launch_nn_q16_t<6, 4, 128, 1>(h, n_q);
-        case 68: return launch_nn_q16_t<4, 4, 128, 1, 3>(h, n_q);      // 62 capped at 85 registers (3 CTAs per SM)
-        case 69: return launch_nn_q16_t<4, 4, 128, 1, 4>(h, n_q);      // 62 capped at 64 registers (4 CTAs per SM)
+        case 56: return launch_nn_q16_t<2, 4, 64, 0, 3>(h, n_q);
+        case 57: return launch_nn_q16_t<4, 4, 32, 0, 3>(h, n_q);
+        // q16, split loops (packed adds as IMAD on the fma pipe + VIMNMX3 on the alu pipe), 4 queries/thread,
+        // <= 80 registers (3 CTAs per SM): 60 = ptxas' own IMAD/IADD3 balance, 61 = 3 IMAD + 1 VIADD.16x2 + 2
+        // VIMNMX3, 62 = 2 VIADDMNMX + 2 IMAD + 1 VIMNMX3, 63 = 4 IMAD + 2 VIMNMX3 (per 8 vertices), 128-vertex
+        // chunks; 64..67 = the same with 64-vertex chunks; 66 Morton order inside a tile (with 62's loop);
+        // 68, 69 = 62 with 8 / 2 queries per thread; 58 = 62 without the global pruning bound
+        case 60: return launch_nn_q16_t<4, 4, 128, 1, 3>(h, n_q);
+        case 61: return launch_nn_q16_t<4, 4, 128, 2, 3>(h, n_q);
+        case 62: case 66: case 58: return launch_nn_q16_t<4, 4, 128, 3, 3>(h, n_q);
+        case 63: return launch_nn_q16_t<4, 4, 128, 4, 3>(h, n_q);
+        case 64: return launch_nn_q16_t<4, 4, 64, 1, 3>(h, n_q);
+        case 65: return launch_nn_q16_t<4, 4, 64, 2, 3>(h, n_q);
+        case 67: return launch_nn_q16_t<4, 4, 64, 3, 3>(h, n_q);
+        case 68: return launch_nn_q16_t<8, 4, 128, 3>(h, n_q);
+        case 69: return launch_nn_q16_t<2, 4, 128, 3, 3>(h, n_q);
         case 40: return launch_nn_slab_t<4, 3, 32>(h, n_q);
         case 41: return launch_nn_slab_t<8, 3, 32>(h, n_q);
         case 42: return launch_nn_slab_t<4, 3, 64>(h, n_q);
@@ -2059,7 +2066,23 @@ int icp_set_base_triangles(icp_handle* h, const float* tri_xyz, int64_t n_local,
     return ICP_OK;
 }
 
+static int set_moving_impl(icp_handle* h, const float* xyz, int64_t n_vertices, const int32_t* vlist, int64_t n_vlist,
+                           bool collective);
+
 int icp_set_moving(icp_handle* h, const float* xyz, int64_t n_vertices, const int32_t* vlist, int64_t n_vlist)
+{
+    return set_moving_impl(h, xyz, n_vertices, vlist, n_vlist, false);
+}
+
+int icp_set_moving_collective(icp_handle* h, const float* xyz, int64_t n_vertices, const int32_t* vlist, int64_t n_vlist)
+{
+    if (h && h->prm.world_size > 1 && !h->comm)
+        return fail(h, ICP_ERR_STATE, "icp_set_moving_collective: icp_comm_init was not called");
+    return set_moving_impl(h, xyz, n_vertices, vlist, n_vlist, h && h->prm.world_size > 1);
+}
+
+static int set_moving_impl(icp_handle* h, const float* xyz, int64_t n_vertices, const int32_t* vlist, int64_t n_vlist,
+                           bool collective)
 {
     if (!h) return ICP_ERR_BAD_ARG;
     if (n_vertices < 0 || (n_vertices > 0 && !xyz) || n_vlist < 0 || (vlist == nullptr && n_vlist != 0))
@@ -2070,7 +2093,11 @@ int icp_set_moving(icp_handle* h, const float* xyz, int64_t n_vertices, const in
             if (vlist[i] < 0 || vlist[i] >= n_vertices)
                 return fail(h, ICP_ERR_BAD_ARG, "icp_set_moving: vlist[%lld] = %d out of range", (long long)i, vlist[i]);
     CUDA_TRY(h, cudaSetDevice(h->prm.device));
-    int rc = ensure(h, h->d_mov, h->mov_capacity, n_vertices * 3);
+    // collective upload: the coordinate array is cut into world_size slices of `per` floats (16-byte
+    // multiples); this rank sends its own slice over the host link and ncclAllGather fills in the rest
+    const long long W = h->prm.world_size;
+    const long long per = collective ? ((n_vertices * 3 + W - 1) / W + 3) / 4 * 4 : 0;
+    int rc = ensure(h, h->d_mov, h->mov_capacity, collective ? per * W : n_vertices * 3);
     if (rc) { h->have_moving = false; return rc; }
     if (vlist) {
         rc = ensure(h, h->d_vlist, h->vlist_capacity, n_vlist);
@@ -2085,8 +2112,14 @@ int icp_set_moving(icp_handle* h, const float* xyz, int64_t n_vertices, const in
                                         (n_vlist == 0 || memcmp(h->h_vlist.data(), vlist, (size_t)n_vlist * sizeof(int32_t)) == 0)));
     const bool same_shape = h->have_moving && h->order_valid && n_vertices == h->n_vertices && same_vlist;
     h->have_moving = false;                          // until every copy below has been queued
-    if (n_vertices > 0)
+    if (n_vertices > 0 && !collective) {
         CUDA_TRY(h, cudaMemcpyAsync(h->d_mov, xyz, (size_t)n_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    } else if (n_vertices > 0) {
+        const long long lo = per * h->prm.rank, hi = std::min<long long>(lo + per, n_vertices * 3);
+        if (hi > lo)
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_mov + lo, xyz + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        NCCL_TRY(h, g_nccl.AllGather(h->d_mov + lo, h->d_mov, (size_t)per, ncclFloat, h->comm, h->stream));
+    }
     if (vlist && n_vlist > 0 && !same_vlist)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_vlist, vlist, (size_t)n_vlist * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     // moments are accumulated about the first vertex of the (replicated) moving array, so that

@@ -180,68 +180,105 @@ __device__ __forceinline__ uint32_t iadd_fma(uint32_t a, uint32_t b)
     return r;
 }
 
+// a + b as IMAD a * one + b with a run-time multiplier (== 1): stays on the fma pipe for certain
+__device__ __forceinline__ uint32_t imad_add(uint32_t a, uint32_t one, uint32_t b)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+
 __device__ __forceinline__ float q16_radius(float best)
 {
     // sqrtf is correctly rounded; 1.000001 covers S4's own roundings (see the header comment)
     return __fmul_rn(sqrtf(best), 1.000001f);
 }
 
-// Slow path, warp-cooperative: ALL 32 lanes re-check one (query, chunk) pair together.  The owner's
-// query is broadcast by the caller; every lane tests CH / 64 words (two vertices each) of the chunk
-// against the 3-axis integer box (three VIADDMNMX + one VIMNMX3.U16x2 per word), lanes whose vertices
-// fall inside evaluate the exact S4 metric on the exact tile in global memory, and the smallest 64-bit
-// key is reduced over the warp: ~100 warp instructions per triggered (query, chunk), whatever CH is.
+// any vertex of the chunk inside the query's interval along one axis?  (chunk = n_words words of `plane`)
+__device__ __forceinline__ bool q16_chunk_any(const uint32_t* plane, int n_words, uint32_t nlo, uint32_t wp)
+{
+    const uint4* p4 = reinterpret_cast<const uint4*>(plane);
+    uint32_t m0 = wp, m1 = wp;
+#pragma unroll 4
+    for (int g = 0; g < n_words / 4; ++g) {
+        const uint4 v = p4[g];
+        m0 = __viaddmin_u16x2(v.x, nlo, m0);
+        m1 = __viaddmin_u16x2(v.y, nlo, m1);
+        m0 = __viaddmin_u16x2(v.z, nlo, m0);
+        m1 = __viaddmin_u16x2(v.w, nlo, m1);
+    }
+    return m0 != wp || m1 != wp;
+}
+
+// Slow path (out of line, every lane for its own query -- the lanes of a warp are neighbours and
+// mostly trigger on the same chunks together): one query against one chunk of n_words * 2 vertices.
 //   tile : the shared-memory tile (planes a | b | c, header)      w0 : first word of the chunk
 //   ex   : the same chunk of the exact tile (global: x | y | z | original index planes)
-//   T    : the query's pruning radius.   Returns the best key found in the chunk, or KEY_NONE.
-template <int CH>
-__device__ __forceinline__ unsigned long long q16_recheck_warp(const uint32_t* tile, const Q16Hdr& hd, int w0,
-                                                               const float* __restrict__ ex, float qa, float qb,
-                                                               float qc, float T, int axes, uint32_t index_offset,
-                                                               int lane)
+//   T    : the query's pruning radius;  flags = axes | (slab axis was b) << 8
+// Stage 1: the OTHER in-plane axis, chunk level (one VIADDMNMX per word).  Stage 2: the third axis.
+// Stage 3: the 3-axis box per vertex, and the exact S4 metric on the vertices inside it.
+__device__ __noinline__ unsigned long long q16_recheck(const uint32_t* tile, int w0, int n_words,
+                                                       const float* __restrict__ ex, float qa, float qb,
+                                                       float qc, float T, int flags, uint32_t index_offset,
+                                                       unsigned long long bkey)
 {
     const float inf = __int_as_float(0x7f800000);
-    const int axis_a = axes & 3, axis_b = (axes >> 2) & 3;
+    const Q16Hdr hd = *reinterpret_cast<const Q16Hdr*>(tile + 3 * Q16_PLANE_WORDS);
+    const bool slab_b = (flags >> 8) & 1;
+    const uint32_t* pa = tile + w0;
+    const uint32_t* pb = pa + Q16_PLANE_WORDS;
+    const uint32_t* pc = pb + Q16_PLANE_WORDS;
+    uint32_t na, wa, nb, wb, nc, wc;
+    if (slab_b) {
+        q16_setup(qa, T, hd.lo_a, hd.inv_a, na, wa);
+        if (wa == 0u || !q16_chunk_any(pa, n_words, na, wa)) return bkey;
+    } else {
+        q16_setup(qb, T, hd.lo_b, hd.inv_b, nb, wb);
+        if (wb == 0u || !q16_chunk_any(pb, n_words, nb, wb)) return bkey;
+    }
+    q16_setup(qc, T, hd.lo_c, hd.inv_c, nc, wc);
+    if (wc == 0u || !q16_chunk_any(pc, n_words, nc, wc)) return bkey;
+    if (slab_b) q16_setup(qb, T, hd.lo_b, hd.inv_b, nb, wb);
+    else q16_setup(qa, T, hd.lo_a, hd.inv_a, na, wa);
+    if (wa == 0u || wb == 0u) return bkey;
+    const int axis_a = flags & 3, axis_b = (flags >> 2) & 3;
     const float ox = axis_a == 0 ? qa : (axis_b == 0 ? qb : qc);
     const float oy = axis_a == 1 ? qa : (axis_b == 1 ? qb : qc);
     const float oz = axis_a == 2 ? qa : (axis_b == 2 ? qb : qc);
-    uint32_t na, wa, nb, wb, nc, wc;
-    q16_setup(qa, T, hd.lo_a, hd.inv_a, na, wa);
-    q16_setup(qb, T, hd.lo_b, hd.inv_b, nb, wb);
-    q16_setup(qc, T, hd.lo_c, hd.inv_c, nc, wc);
-    unsigned long long best = KEY_NONE;
-    if (wa != 0u && wb != 0u && wc != 0u) {          // warp-uniform: every lane holds the same query
-        const uint32_t fa = ~wa, fb = ~wb, fc = ~wc; // per half: 0xFFFF - W
-        constexpr int WPC = CH / 2;                  // words per chunk
+    uint32_t fa = ~wa, fb = ~wb, fc = ~wc;          // per half: 0xFFFF - W
+    for (int w = 0; w < n_words; ++w) {
+        // per half: e in [0, W], e < W iff inside; e + (0xFFFF - W) < 0xFFFF iff inside (no carry)
+        const uint32_t ea = __viaddmin_u16x2(pa[w], na, wa) + fa;
+        const uint32_t eb = __viaddmin_u16x2(pb[w], nb, wb) + fb;
+        const uint32_t ec = __viaddmin_u16x2(pc[w], nc, wc) + fc;
+        const uint32_t f = __vimax3_u16x2(ea, eb, ec);
+        if (f == 0xFFFFFFFFu) continue;             // neither vertex of the word is inside the box
+        bool improved = false;
 #pragma unroll
-        for (int j = 0; j * 32 < WPC; ++j) {
-            const int wl = lane + 32 * j;
-            if (WPC % 32 != 0 && wl >= WPC) break;
-            const uint32_t* pw = tile + w0 + wl;
-            // per half: e in [0, W], e < W iff inside; e + (0xFFFF - W) < 0xFFFF iff inside (no carry)
-            const uint32_t ea = __viaddmin_u16x2(pw[0], na, wa) + fa;
-            const uint32_t eb = __viaddmin_u16x2(pw[Q16_PLANE_WORDS], nb, wb) + fb;
-            const uint32_t ec = __viaddmin_u16x2(pw[2 * Q16_PLANE_WORDS], nc, wc) + fc;
-            const uint32_t f = __vimax3_u16x2(ea, eb, ec);
-            if (f == 0xFFFFFFFFu) continue;          // neither vertex of the word is inside the box
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                if (((f >> (16 * half)) & 0xFFFFu) == 0xFFFFu) continue;
-                const int i = 2 * wl + half;         // index inside the chunk
-                const float d = s4_d2(ox, oy, oz, ex[i], ex[NN_TILE + i], ex[2 * NN_TILE + i]);
-                if (d < inf) {
-                    const unsigned long long k =
-                        ((unsigned long long)__float_as_uint(d) << 32) |
-                        (unsigned long long)(index_offset + __float_as_uint(ex[3 * NN_TILE + i]));
-                    best = k < best ? k : best;
-                }
+        for (int half = 0; half < 2; ++half) {
+            if (((f >> (16 * half)) & 0xFFFFu) == 0xFFFFu) continue;
+            const int i = 2 * w + half;                          // index inside the chunk
+            const float d = s4_d2(ox, oy, oz, ex[i], ex[NN_TILE + i], ex[2 * NN_TILE + i]);
+            if (d < inf) {
+                const unsigned long long k =
+                    ((unsigned long long)__float_as_uint(d) << 32) |
+                    (unsigned long long)(index_offset + __float_as_uint(ex[3 * NN_TILE + i]));
+                if (k < bkey) { bkey = k; improved = true; }
+            }
+        }
+        if (improved) {                             // a nearer real vertex: tighter box for the rest of the chunk
+            const float T2 = q16_radius(key_d2(bkey));
+            if (T2 < T) {
+                T = T2;
+                q16_setup(qa, T, hd.lo_a, hd.inv_a, na, wa);
+                q16_setup(qb, T, hd.lo_b, hd.inv_b, nb, wb);
+                q16_setup(qc, T, hd.lo_c, hd.inv_c, nc, wc);
+                if (wa == 0u || wb == 0u || wc == 0u) return bkey;
+                fa = ~wa; fb = ~wb; fc = ~wc;
             }
         }
     }
-    const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
-    const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
-    const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
-    return ((unsigned long long)mhi << 32) | (unsigned long long)mlo;
+    return bkey;
 }
 
 // grid.x = query blocks of NN_THREADS * R slots, grid.y = base ranges of tiles_per_cta tiles.
@@ -249,8 +286,9 @@ __device__ __forceinline__ unsigned long long q16_recheck_warp(const uint32_t* t
 // `bound` (nullable): per-slot squared pruning radius from another source than the seed (the global
 // winner of the previous pass moved by the query's displacement, when the base is sharded).
 // MIX = 0: one VIADDMNMX.U16x2 per word (2 vertices), alu pipe only: 2.0 cycles per warp instruction.
-// MIX = 1: two IMAD adds (fma pipe) + one VIMNMX3.U16x2 (alu pipe) per two words (4 vertices): the pipes
-//          overlap, 2.65 cycles per 4 vertices against 4.0 (tools/ubench/pipes3.cu).
+// MIX >= 1: the packed add moves (partly) to the fma pipe as IMAD and VIMNMX3.U16x2 folds two sums per
+//          instruction; both are 2-cycle instructions on 16-lane pipes (IMAD runs on fmaheavy only), so the
+//          mixes differ in how they balance alu / fmaheavy / issue slots -- see the loop body.
 template <int R, int STAGES, int CH, int MIX, int MINB>
 __global__ void __launch_bounds__(NN_THREADS, MINB)
 k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict__ etiles, int axes,
@@ -286,12 +324,14 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
     }
 
     const int axis_a = axes & 3, axis_b = (axes >> 2) & 3, axis_c = (axes >> 4) & 3;
-    const long long q0 = (long long)blockIdx.x * (NN_THREADS * R) + tid;
+    // R CONSECUTIVE slots per thread: slots are in Morton order of the moving vertices, so a warp's
+    // 32 R queries form one compact patch and one slab axis per (warp, tile) suits all of them
+    const long long q0 = (long long)blockIdx.x * (NN_THREADS * R) + (long long)tid * R;
     float qa[R], qb[R], qc[R], bnd[R], rad[R];      // bnd: squared pruning radius, rad: its root (< 0: padding slot)
     unsigned long long bkey[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const long long p = q0 + (long long)r * NN_THREADS;
+        const long long p = q0 + r;
         const bool ok = p < n_queries;
         const float x = ok ? qx[p] : 0.0f, y = ok ? qy[p] : 0.0f, z = ok ? qz[p] : 0.0f;
         qa[r] = axis_of(x, y, z, axis_a); qb[r] = axis_of(x, y, z, axis_b); qc[r] = axis_of(x, y, z, axis_c);
@@ -303,6 +343,9 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
         if (ok && bound != nullptr) bnd[r] = fminf(bnd[r], bound[p]);
         rad[r] = ok ? q16_radius(bnd[r]) : -1.0f;    // padding slot: q16_setup answers "never"
     }
+    // a multiplier ptxas cannot prove to be 1: keeps the packed adds on the fma pipe (IMAD) instead of
+    // letting it turn them into IADD3 on the alu pipe, which the min instructions need
+    const uint32_t one = ((uint32_t)n_tiles >> 30) | 1u;
 
     for (int it = 0; it < my_tiles; ++it) {
         const int slot = it % STAGES;
@@ -310,12 +353,12 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
         const uint32_t* tile = reinterpret_cast<const uint32_t*>(smem_raw + (size_t)slot * TILE_STRIDE);
         const Q16Hdr hd = *reinterpret_cast<const Q16Hdr*>(tile + 3 * Q16_PLANE_WORDS);
         // slab axis of this (warp, tile): the one along which most lanes are farther from the tile centre
-        const bool use_b = __popc(__ballot_sync(0xffffffffu, fabsf(qb[0] - hd.cen_b) > fabsf(qa[0] - hd.cen_a))) > 16;
+        const bool use_b = __popc(__ballot_sync(0xffffffffu, fabsf(qb[R / 2] - hd.cen_b) > fabsf(qa[R / 2] - hd.cen_a))) > 16;
         const float lo_s = use_b ? hd.lo_b : hd.lo_a, inv_s = use_b ? hd.inv_b : hd.inv_a;
         uint32_t nlo[R], wp[R];
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            q16_setup<MIX == 1>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
+            q16_setup<MIX != 0>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
         const uint4* plane = reinterpret_cast<const uint4*>(tile + (use_b ? Q16_PLANE_WORDS : 0));
 #pragma unroll 1
         for (int c = 0; c < NN_TILE / CH; ++c) {
@@ -327,41 +370,44 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
                 const uint4 v = plane[c * (CH / 8) + g];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (MIX == 0) {
+                    if (MIX == 0) {             // alu pipe only: 4 VIADDMNMX
                         acc[r] = __viaddmin_u16x2(v.x, nlo[r], acc[r]);
                         acc[r] = __viaddmin_u16x2(v.y, nlo[r], acc[r]);
                         acc[r] = __viaddmin_u16x2(v.z, nlo[r], acc[r]);
                         acc[r] = __viaddmin_u16x2(v.w, nlo[r], acc[r]);
-                    } else {
+                    } else if (MIX == 1) {      // 4 adds left to ptxas' own IMAD / IADD3 balance + 2 VIMNMX3
                         acc[r] = __vimin3_u16x2(acc[r], iadd_fma(v.x, nlo[r]), iadd_fma(v.y, nlo[r]));
                         acc[r] = __vimin3_u16x2(acc[r], iadd_fma(v.z, nlo[r]), iadd_fma(v.w, nlo[r]));
+                    } else if (MIX == 2) {      // 3 IMAD (fma pipe) + 1 VIADD.16x2 + 2 VIMNMX3 (alu pipe): 6 + 6 cycles
+                        acc[r] = __vimin3_u16x2(acc[r], imad_add(v.x, one, nlo[r]), imad_add(v.y, one, nlo[r]));
+                        acc[r] = __vimin3_u16x2(acc[r], imad_add(v.z, one, nlo[r]), __vadd2(v.w, nlo[r]));
+                    } else if (MIX == 3) {      // 2 VIADDMNMX + 2 IMAD + 1 VIMNMX3: 5 instructions, alu 6 / fma 4 cycles
+                        acc[r] = __viaddmin_u16x2(v.x, nlo[r], acc[r]);
+                        acc[r] = __vimin3_u16x2(acc[r], imad_add(v.y, one, nlo[r]), imad_add(v.z, one, nlo[r]));
+                        acc[r] = __viaddmin_u16x2(v.w, nlo[r], acc[r]);
+                    } else {                    // MIX 4: all four adds as IMAD with the opaque multiplier + 2 VIMNMX3
+                        acc[r] = __vimin3_u16x2(acc[r], imad_add(v.x, one, nlo[r]), imad_add(v.y, one, nlo[r]));
+                        acc[r] = __vimin3_u16x2(acc[r], imad_add(v.z, one, nlo[r]), imad_add(v.w, one, nlo[r]));
                     }
                 }
             }
             bool trig = false;
 #pragma unroll
             for (int r = 0; r < R; ++r) trig = trig || (acc[r] != wp[r]);
-            if (__any_sync(0xffffffffu, trig)) {
-                // all lanes serve the triggered (lane, query) pairs of this chunk one after the other
+            if (trig) {
                 const float* ex = etiles + (size_t)(t0 + it) * CYL_TILE_FLOATS + c * CH;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    unsigned todo = __ballot_sync(0xffffffffu, acc[r] != wp[r]);
-                    while (todo) {
-                        const int src = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const float sa = __shfl_sync(0xffffffffu, qa[r], src), sb = __shfl_sync(0xffffffffu, qb[r], src),
-                                    sc = __shfl_sync(0xffffffffu, qc[r], src), sT = __shfl_sync(0xffffffffu, rad[r], src);
-                        const unsigned long long k = q16_recheck_warp<CH>(tile, hd, c * (CH / 2), ex, sa, sb, sc, sT, axes,
-                                                                          index_offset, lane);
-                        if (lane == src && k < bkey[r]) {
-                            bkey[r] = k;
-                            const float d = key_d2(k);
-                            if (d < bnd[r]) {
-                                bnd[r] = d;
-                                rad[r] = q16_radius(d);
-                                q16_setup<MIX == 1>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
-                            }
+                    if (acc[r] == wp[r]) continue;
+                    const unsigned long long k = q16_recheck(tile, c * (CH / 2), CH / 2, ex, qa[r], qb[r], qc[r], rad[r],
+                                                             axes | (use_b ? 256 : 0), index_offset, bkey[r]);
+                    if (k != bkey[r]) {
+                        bkey[r] = k;
+                        const float d = key_d2(k);
+                        if (d < bnd[r]) {
+                            bnd[r] = d;
+                            rad[r] = q16_radius(d);
+                            q16_setup<MIX != 0>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
                         }
                     }
                 }
@@ -379,7 +425,7 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const long long p = q0 + (long long)r * NN_THREADS;
+        const long long p = q0 + r;
         if (p < n_queries && bkey[r] != KEY_NONE) atomicMin(&keys[p], bkey[r]);
     }
 }

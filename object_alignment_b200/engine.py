@@ -167,6 +167,16 @@ class IcpEngine:
         else:
             self._check(self._lib.icp_set_moving(self._h, xyz.ctypes.data, xyz.shape[0], None, 0))
 
+    def set_moving_collective(self, xyz, vlist=None):
+        """Collective upload (every rank calls it with the same array): 1/world_size of the coordinates
+        over this rank's host link, the rest over NVLink (ncclAllGather)."""
+        xyz = _f32c(xyz, (-1, 3))
+        if vlist is not None:
+            vlist = np.ascontiguousarray(vlist, dtype=np.int32)
+        self._check(self._lib.icp_set_moving_collective(
+            self._h, xyz.ctypes.data, xyz.shape[0], None if vlist is None else vlist.ctypes.data,
+            0 if vlist is None else vlist.shape[0]))
+
     def set_moving_sharded(self, xyz, vlist=None):
         """ICP_SHARD_QUERIES: this rank keeps only its contiguous slice of the sampled query
         positions (the stride is applied here, once, so every rank samples the same vertices)."""
