@@ -33,11 +33,12 @@ __all__ = ["VertexNN", "SurfaceNN", "base_index_from_object", "extract_triangles
 
 
 # ----------------------------------------------------------------------------- marshalling
-def extract_coords(obj) -> np.ndarray:
-    """(n, 3) float32 vertex coordinates of ``obj.data.vertices`` (bulk foreach_get if present)."""
+def extract_coords(obj, out=None) -> np.ndarray:
+    """(n, 3) float32 vertex coordinates of ``obj.data.vertices`` (bulk foreach_get if present).
+    ``out``: a flat float32 buffer of 3 n elements to fill instead of a fresh array (pinned staging)."""
     verts = obj.data.vertices
     n = len(verts)
-    buf = np.empty(n * 3, dtype=np.float32)
+    buf = np.empty(n * 3, dtype=np.float32) if out is None else out
     if hasattr(verts, "foreach_get"):
         verts.foreach_get("co", buf)
     else:

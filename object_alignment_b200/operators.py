@@ -18,9 +18,9 @@ import time
 import numpy as np
 
 from . import _native as N
-from .engine import IcpError, stride_from_sample_fraction
-from .functions import (array_to_matrix_like, base_index_from_object, extract_coords,
-                        matrix_to_array)
+from .engine import IcpError, PinnedArray, stride_from_sample_fraction
+from .functions import (affine_matrix_from_points, array_to_matrix_like, base_index_from_object,
+                        extract_coords, matrix_to_array)
 from .preferences import get_addon_preferences
 
 try:  # inside Blender
@@ -85,10 +85,10 @@ def build_vlist_from_arrays(n_verts, groups) -> np.ndarray:
 def _apply_to_m_objects(context, new_mats):
     """take_m_with (icp_align.py:123-127): post-multiply every scene object named 'm_*'."""
     scene_objects = None
-    if bpy is not None:
-        scene_objects = bpy.context.scene.objects
-    elif hasattr(context, "scene"):
+    if getattr(context, "scene", None) is not None:
         scene_objects = context.scene.objects
+    elif bpy is not None:
+        scene_objects = bpy.context.scene.objects        # what the reference reads (icp_align.py:124)
     if not scene_objects:
         return
     for obj in scene_objects:
@@ -96,6 +96,68 @@ def _apply_to_m_objects(context, new_mats):
             for nm in new_mats:
                 obj.matrix_world = obj.matrix_world @ array_to_matrix_like(nm, obj.matrix_world)
             obj.update_tag()
+
+
+def upload_moving_pinned(engine, align_obj, vlist):
+    """foreach_get("co") straight into page-locked memory, then icp_set_moving from it: the upload
+    runs at the full host-link rate with no intermediate pageable copy."""
+    n = len(align_obj.data.vertices)
+    staging = PinnedArray((max(n, 1), 3), np.float32)
+    try:
+        coords = extract_coords(align_obj, out=staging.array.reshape(-1)[:3 * n])
+        engine.set_moving(coords, vlist)          # returns after the copy has completed
+    finally:
+        staging.close()
+
+
+class OBJECT_OT_align_pick_points(Operator):
+    """Align two objects with 3 or more pairs of picked points (GPU solver)"""
+    # SURVEY section 8f row N4: the arithmetic of the reference's picked-points operator
+    # (operators/align_pick_points.py:415-465).  Its split-view picking UI (invoke / modal / draw
+    # callbacks, :106-357) is interactive bpy code and stays the addon's own; it fills
+    # `align_points`, `base_points` (both in align-local space, :162,184) and `obj_align`, then calls
+    # `align_obj`, which is what this class provides on top of icp_solve_pairs.
+    bl_idname = "object.align_picked_points"
+    bl_label = "Align: Picked Points"
+    bl_options = {'REGISTER', 'UNDO'}
+
+    def __init__(self, obj_align=None, align_points=(), base_points=()):
+        self.obj_align = obj_align
+        self.align_points = list(align_points)
+        self.base_points = list(base_points)
+
+    @classmethod
+    def poll(cls, context):
+        condition_1 = len(context.selected_objects) == 2
+        condition_2 = context.object.type == 'MESH'
+        return condition_1 and condition_2
+
+    def align_obj(self, context):
+        # unequal lists are cut to the shorter one (align_pick_points.py:417-422)
+        if len(self.align_points) != len(self.base_points):
+            if len(self.align_points) < len(self.base_points):
+                self.base_points = self.base_points[0:len(self.align_points)]
+            else:
+                self.align_points = self.align_points[0:len(self.base_points)]
+        k = len(self.base_points)
+        A = np.zeros(shape=[3, k])
+        B = np.zeros(shape=[3, k])
+        for i in range(k):
+            V1, V2 = self.align_points[i], self.base_points[i]
+            A[0][i], A[1][i], A[2][i] = V1[0], V1[1], V1[2]
+            B[0][i], B[1][i], B[2][i] = V2[0], V2[1], V2[2]
+        settings = get_addon_preferences()
+        # ValueError("input arrays are of wrong shape or type") below 3 pairs, like the reference's solver
+        M = affine_matrix_from_points(A, B, shear=False, scale=(settings.align_meth == '1'), usesvd=True)
+        new_mat = M.astype(np.float32)                                        # :446-449, fp64 -> fp32
+        self.obj_align.matrix_world = self.obj_align.matrix_world @ array_to_matrix_like(
+            new_mat, self.obj_align.matrix_world)                             # :453
+        if settings.take_m_with:
+            _apply_to_m_objects(context, [new_mat])                          # :455-459
+        self.obj_align.update_tag()
+        context.view_layer.update()
+        self.M = M
+        return M
 
 
 class OBJECT_OT_icp_align(Operator):
@@ -135,7 +197,7 @@ class OBJECT_OT_icp_align(Operator):
             align_meth=settings.align_meth, stride=factor, reject_fraction=self.reject_fraction)
         try:
             eng = base_nn.engine
-            eng.set_moving(extract_coords(align_obj), vlist)
+            upload_moving_pinned(eng, align_obj, vlist)
             eng.set_matrices(matrix_to_array(align_obj.matrix_world),
                              matrix_to_array(base_obj.matrix_world))
             try:
@@ -212,7 +274,7 @@ class OBJECT_OT_icp_align_feedback(Operator):
             stride=stride_from_sample_fraction(settings.sample_fraction),
             reject_fraction=self.reject_fraction)
         eng = self.base_nn.engine
-        eng.set_moving(extract_coords(self.align_obj), self.vlist)
+        upload_moving_pinned(eng, self.align_obj, self.vlist)
         eng.set_matrices(matrix_to_array(self.align_obj.matrix_world),
                          matrix_to_array(self.base_obj.matrix_world))
         self.total_iters = 0

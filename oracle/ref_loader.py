@@ -5,7 +5,7 @@ Runs the files under ``/root/reference`` (this container) or their staged byte-f
 ``oracle/gen_golden.py`` to produce ``tests/golden/*.npz`` and by the CPU tests that pin
 ``oracle/icp_oracle.py`` against the live reference when it is present.
 
-Nothing from the reference is copied: its modules are executed from where they lie.
+Nothing from the reference enters the repo's history: its modules are executed from where they lie.
 The stubs exist because ``functions/general.py:26`` star-imports ``functions/common``,
 whose modules import ``bpy``/``bmesh``/``mathutils`` and read ``bpy.app.version`` at import
 time (functions/common/blender.py:24-30, wrappers.py:45), and ``operators/icp_align.py``
@@ -20,6 +20,7 @@ import types
 import warnings
 
 from . import mathutils_shim as ms
+
 
 def _find_root():
     """ICP_REFERENCE_ROOT, else the read-only checkout, else the staged copy (oracle/stage_ref.py)."""
@@ -92,10 +93,13 @@ def _install_stubs():
     for fn in ("location_3d_to_region_2d", "region_2d_to_vector_3d", "region_2d_to_origin_3d"):
         setattr(view3d_utils, fn, lambda *a, **k: None)
     bpy_extras.view3d_utils = view3d_utils
+    gpu_extras = _module("gpu_extras")
+    gpu_batch = _module("gpu_extras.batch", batch_for_shader=lambda *a, **k: None)   # align_pick_points.py:29
+    gpu_extras.batch = gpu_batch
     mods = {
         "bpy": bpy, "bpy.types": bpy_types, "bpy.props": bpy_props,
         "bmesh": _module("bmesh"), "bgl": _module("bgl"), "blf": _module("blf"),
-        "gpu": _module("gpu"),
+        "gpu": _module("gpu"), "gpu_extras": gpu_extras, "gpu_extras.batch": gpu_batch,
         "mathutils": mathutils, "mathutils.bvhtree": bvhtree,
         "bpy_extras": bpy_extras, "bpy_extras.view3d_utils": view3d_utils,
     }
@@ -112,6 +116,15 @@ def _synthetic_package(name, path):
     pkg.__package__ = name
     sys.modules[name] = pkg
     return pkg
+
+
+def load_pick_points():
+    """The reference's picked-points operator module (operators/align_pick_points.py), for its
+    ``align_obj`` (:415-465) -- the interactive parts are never called."""
+    load_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return importlib.import_module(_PKG + ".operators.align_pick_points")
 
 
 def load_reference():
