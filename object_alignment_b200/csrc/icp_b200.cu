@@ -34,6 +34,7 @@
 #include "nn_bruteforce_slab.cuh"
 #include "nn_bruteforce_q16.cuh"
 #include "nn_bvh.cuh"
+#include "nn_tiletree.cuh"
 #include "nn_surface.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -779,6 +780,12 @@ struct icp_handle {
     float4* d_bvh_sorted = nullptr;
     int bvh_P = 0;
     bool bvh_built = false;
+    // 32-ary tree of Morton tiles over the same sorted vertices (nn_tiletree.cuh; default tree search)
+    float4* d_tt_boxes = nullptr;
+    float* d_tt_tiles = nullptr;
+    TileTree* d_tt_desc = nullptr;
+    TileTree tt{};
+    bool tt_built = false;
     // query slots in Morton order of the moving vertices (BVH mode) + warm start bookkeeping
     uint32_t* d_slot_pos = nullptr;
     uint32_t* d_pos_slot = nullptr;
@@ -1418,17 +1425,64 @@ int build_bvh(icp_handle* h)
     return ICP_OK;
 }
 
+// tile tree over the Morton-sorted vertices build_bvh leaves in d_bvh_sorted (one-time per base)
+int build_tiletree(icp_handle* h)
+{
+    if (h->tt_built) return ICP_OK;
+    int rc = build_bvh(h);
+    if (rc) return rc;
+    for (void* p : {(void*)h->d_tt_boxes, (void*)h->d_tt_tiles}) if (p) cudaFree(p);
+    h->d_tt_boxes = nullptr; h->d_tt_tiles = nullptr;
+    memset(&h->tt, 0, sizeof(h->tt));
+    const long long n = h->n_local;
+    if (n > 0) {
+        int total = 0, c = (int)((n + TT_LEAF - 1) / TT_LEAF), levels = 0;
+        while (true) {
+            h->tt.count[levels] = c; h->tt.offset[levels] = total; total += c; ++levels;
+            if (c <= TT_FAN || levels == TT_MAX_LEVELS) break;
+            c = (c + TT_FAN - 1) / TT_FAN;
+        }
+        if (h->tt.count[levels - 1] > TT_FAN) return fail(h, ICP_ERR_BAD_ARG, "tile tree: too many vertices");
+        h->tt.n_levels = levels;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_boxes, (size_t)total * 2 * sizeof(float4)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_tiles, (size_t)h->tt.count[0] * TT_TILE_FLOATS * sizeof(float)));
+        k_tt_build_tiles<<<(unsigned)(((long long)h->tt.count[0] * 32 + 255) / 256), 256, 0, h->stream>>>(
+            h->d_bvh_sorted, n, h->tt.count[0], h->d_tt_tiles, h->d_tt_boxes);
+        for (int l = 1; l < levels; ++l)
+            k_tt_build_level<<<(unsigned)(((long long)h->tt.count[l] * 32 + 255) / 256), 256, 0, h->stream>>>(
+                h->d_tt_boxes + 2 * (size_t)h->tt.offset[l - 1], h->tt.count[l - 1],
+                h->d_tt_boxes + 2 * (size_t)h->tt.offset[l], h->tt.count[l]);
+        h->launches += levels;
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    h->tt.boxes = h->d_tt_boxes;
+    h->tt.tiles = h->d_tt_tiles;
+    if (!h->d_tt_desc) CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_desc, sizeof(TileTree)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_tt_desc, &h->tt, sizeof(TileTree), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->tt_built = true;
+    return ICP_OK;
+}
+
+// vertex tree searches: 0 (default) = warp walk over the 32-ary tile tree; 12 = binary LBVH packet walk;
+// 10 = LBVH per-thread walk; 98, 99 = LBVH walks with visit counters
+bool tiletree_variant(const icp_handle* h) { return h->prm.nn_variant == 0 || h->prm.nn_variant == 13; }
+
 int launch_nn_bvh(icp_handle* h, long long n_q)
 {
     if (n_q <= 0 || h->n_local <= 0) return ICP_OK;
-    int rc = build_bvh(h);
+    int rc = tiletree_variant(h) ? build_tiletree(h) : build_bvh(h);
     if (rc) return rc;
     ProfScope ps(h, 0);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     const unsigned g128 = (unsigned)((n_q + 127) / 128);
     const unsigned gpk = (unsigned)((n_q + PKT_THREADS - 1) / PKT_THREADS);
     const int v = h->prm.nn_variant;
-    if (v == 99) {          // debug: per-thread walk with visit counters (icp_debug_counters)
+    if (tiletree_variant(h)) {
+        k_nn_tiletree<false><<<(unsigned)((n_q + TT_THREADS - 1) / TT_THREADS), TT_THREADS, 0, h->stream>>>(
+            h->d_tt_desc, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0, n_q, h->d_keys,
+            (uint32_t)h->base_off, nullptr);
+    } else if (v == 99) {          // debug: per-thread walk with visit counters (icp_debug_counters)
         k_nn_bvh<true><<<g128, 128, 0, h->stream>>>(h->d_bvh_nodes, h->d_bvh_sorted, h->bvh_P, qx, qy, qz, n_q,
                                                     h->d_keys, (uint32_t)h->base_off, &h->d_state->converged);
     } else if (v == 10) {   // per-thread walk
@@ -1697,11 +1751,12 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     if (rc) return rc;
     if (h->surface != (h->prm.nn_mode == ICP_NN_SURFACE))
         return fail(h, ICP_ERR_STATE, "nn_mode ICP_NN_SURFACE needs icp_set_base_triangles (and the vertex modes need icp_set_base)");
+    const bool tiletree = !h->surface && tiletree_variant(h);
     if (!h->surface) {
-        rc = build_bvh(h);
+        rc = tiletree ? build_tiletree(h) : build_bvh(h);
         if (rc) return rc;
     }
-    const int cta = h->surface ? SURF_THREADS : PKT_THREADS;
+    const int cta = h->surface ? SURF_THREADS : (tiletree ? TT_THREADS : PKT_THREADS);
     const int g = (int)std::max<long long>(1, (n_q + cta - 1) / cta);
     rc = ensure_partials(h, g);
     if (rc) return rc;
@@ -1722,6 +1777,11 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
                 h->d_tri_nodes, h->d_tri_sorted, h->n_local > 0 ? h->tri_runs : 0, nullptr, nullptr, nullptr, h->d_state,
                 h->d_mov_slots, h->d_tris4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
                 h->d_keys, (uint32_t)h->base_off, h->tri_extent, h->d_partials);
+        else if (tiletree)
+            k_nn_tiletree<true><<<g, TT_THREADS, 0, h->stream>>>(
+                h->d_tt_desc, nullptr, nullptr, nullptr, h->d_state,
+                h->d_mov_slots, h->d_base4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
+                h->d_keys, (uint32_t)h->base_off, h->d_partials);
         else
             k_nn_bvh_packet<true, false><<<g, PKT_THREADS, 0, h->stream>>>(
                 h->d_bvh_nodes, h->d_bvh_sorted, h->n_local > 0 ? h->bvh_P : 0, nullptr, nullptr, nullptr, h->d_state,
@@ -1939,7 +1999,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound, h->d_tt_boxes, h->d_tt_tiles, h->d_tt_desc};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1974,6 +2034,7 @@ int icp_set_base(icp_handle* h, const float* xyz, int64_t n_local, int64_t globa
     h->n_local = n_local; h->n_global = n_global; h->base_off = global_offset;
     h->surface = false;
     h->bvh_built = false;
+    h->tt_built = false;
     h->filter_built = false;
     h->cyl_sorted = -1;
     h->slab_order = -1;
@@ -2008,7 +2069,8 @@ int icp_set_base_triangles(icp_handle* h, const float* tri_xyz, int64_t n_local,
     h->n_local = n_local; h->n_global = n_global; h->base_off = global_offset;
     h->n_tiles = 0;
     h->surface = true;
-    h->bvh_built = false; h->filter_built = false; h->warm_valid = false; h->bf_warm_valid = false;
+    h->bvh_built = false; h->tt_built = false; h->filter_built = false; h->warm_valid = false; h->bf_warm_valid = false;
+    h->q16_order = -1; h->slab_order = -1; h->cyl_sorted = -1;
     h->tri_runs = 0; h->tri_extent = 0.0f;
     if (n_local > 0) {
         const long long n = n_local;

@@ -1,0 +1,305 @@
+// nn_tiletree.cuh -- row N2 of SURVEY.md section 8f, second form: the exact nearest-vertex search as a
+// warp-cooperative walk over a 32-ary tree of Morton tiles (default of nn_mode ICP_NN_BVH).
+//
+// Replaces the per-vertex `base_bvh.find_nearest(co_find)` of the reference (functions/general.py:297,
+// nearest-VERTEX variant) with an O(M log N) search that returns the same 64-bit keys
+// as the brute-force kernels (float_bits(d2) << 32 | index: ties to the lowest index).
+//
+// Why a second tree: the binary LBVH packet walk (nn_bvh.cuh) spends 12.5 k warp instructions per 32
+// queries -- ~100 dependent node visits, each one two box tests per LANE plus four warp votes.  Here the
+// lanes of a warp change roles by level:
+//   * index  = the base vertices in Morton order, cut into LEAF TILES of 32 vertices stored SoA
+//              (x[32] | y[32] | z[32] | index[32], 512 B), and per level an array of axis-aligned boxes:
+//              level 0 = one box per tile, level l = one box per 32 boxes of level l - 1; the top level has
+//              at most 32 boxes.  Implicit 32-ary tree, no pointers (1M vertices: 31250 / 977 / 31 boxes).
+//   * upper levels: the 32 queries of a warp (neighbours: slots are in Morton order of the moving
+//              vertices) are summarised by ONE patch box = the union of the balls |p - q_i| <= T_i,
+//              T_i = the lane's current best distance.  A group of 32 boxes is tested in one step,
+//              ONE BOX PER LANE against the patch box, one vote.
+//   * leaf tiles: lane = query again.  Every lane folds the 32 vertices of a tile into a running minimum
+//              with packed fp32 math (3 FADD2/FMUL2/FFMA2 + half an FMNMX3 per vertex); only a lane whose
+//              tile minimum reaches its best re-scans the tile for the exact lowest index.
+// A vertex that could beat or tie lane i's best lies inside ball i, hence inside the patch box, hence
+// its tile's box intersects the patch box and the tile is scanned: exact.  T_i carries a 2e-6 relative
+// margin for the fp32 rounding of S4 and of the box arithmetic (like nn_bvh.cuh's BVH_SHRINK).
+// Without a seed (first pass) the warp first descends greedily to the tile nearest its first query and
+// scans it, which gives every lane a finite bound.
+#pragma once
+#include "nn_bruteforce.cuh"
+#include "nn_bvh.cuh"
+
+namespace icp {
+
+constexpr int TT_LEAF = 32;            // vertices per leaf tile
+constexpr int TT_FAN = 32;             // boxes per group = lanes per warp
+constexpr int TT_MAX_LEVELS = 6;       // 32^6 tiles: far beyond the 2^32 - 2 vertex limit of the ABI
+constexpr int TT_TILE_FLOATS = 4 * TT_LEAF;
+constexpr int TT_STACK = TT_MAX_LEVELS * TT_FAN;
+#ifndef ICP_TT_THREADS
+#define ICP_TT_THREADS 128
+#endif
+constexpr int TT_THREADS = ICP_TT_THREADS;
+
+struct TileTree {                      // lives in device memory (the walk indexes count / offset by level)
+    const float4* boxes;               // all levels back to back; box b = boxes[2b] (lo.xyz), boxes[2b+1] (hi.xyz)
+    const float* tiles;                // [tile][x | y | z | index bits][TT_LEAF]
+    int n_levels;
+    int count[TT_MAX_LEVELS];          // boxes per level (level 0 = tiles)
+    int offset[TT_MAX_LEVELS];         // first box of each level inside `boxes`
+};
+
+// sorted (Morton order) float4(x, y, z, index bits), padded with +inf / 0xFFFFFFFF -> SoA tiles + level-0 boxes.
+// One warp per tile (TT_LEAF == 32: one vertex per lane).
+__global__ void k_tt_build_tiles(const float4* __restrict__ sorted, long long n, int n_tiles,
+                                 float* __restrict__ tiles, float4* __restrict__ boxes0)
+{
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= n_tiles) return;
+    const float inf = __int_as_float(0x7f800000);
+    const long long j = (long long)t * TT_LEAF + lane;
+    float4 p = make_float4(inf, inf, inf, __uint_as_float(0xFFFFFFFFu));
+    if (j < n) p = sorted[j];
+    float* tp = tiles + (size_t)t * TT_TILE_FLOATS;
+    tp[lane] = p.x; tp[TT_LEAF + lane] = p.y; tp[2 * TT_LEAF + lane] = p.z; tp[3 * TT_LEAF + lane] = p.w;
+    const bool fin = fabsf(p.x) < inf && fabsf(p.y) < inf && fabsf(p.z) < inf;
+    float lo[3] = {fin ? p.x : inf, fin ? p.y : inf, fin ? p.z : inf};
+    float hi[3] = {fin ? p.x : -inf, fin ? p.y : -inf, fin ? p.z : -inf};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if (lane == 0) {                   // an empty box (no finite vertex) keeps lo = +inf, hi = -inf: never intersected
+        boxes0[2 * (size_t)t] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        boxes0[2 * (size_t)t + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    }
+}
+
+// one warp per output box: the union of up to 32 boxes of the level below
+__global__ void k_tt_build_level(const float4* __restrict__ below, int n_below, float4* __restrict__ above, int n_above)
+{
+    const int g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= n_above) return;
+    const float inf = __int_as_float(0x7f800000);
+    const int c = g * TT_FAN + lane;
+    float4 l = make_float4(inf, inf, inf, 0.f), h = make_float4(-inf, -inf, -inf, 0.f);
+    if (c < n_below) { l = below[2 * (size_t)c]; h = below[2 * (size_t)c + 1]; }
+    float lo[3] = {l.x, l.y, l.z}, hi[3] = {h.x, h.y, h.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if (lane == 0) {
+        above[2 * (size_t)g] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        above[2 * (size_t)g + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    }
+}
+
+// order-preserving float <-> uint (for redux.sync min / max on floats, NaN-free inputs)
+__device__ __forceinline__ uint32_t tt_f2o(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float tt_o2f(uint32_t o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+__device__ __forceinline__ float tt_warp_min(float v) { return tt_o2f(__reduce_min_sync(0xffffffffu, tt_f2o(v))); }
+__device__ __forceinline__ float tt_warp_max(float v) { return tt_o2f(__reduce_max_sync(0xffffffffu, tt_f2o(v))); }
+
+constexpr float TT_GROW = 1.000002f;   // 2e-6 relative on the radius: > the fp32 rounding of S4 (5 ulp) and of the box tests
+
+// Scan one leaf tile for this lane's query: running minimum with packed math, exact key on demand.
+__device__ __forceinline__ void tt_scan_tile(const float* __restrict__ tp, float x, float y, float z,
+                                             uint32_t index_offset, unsigned long long& best, float& best_d)
+{
+    const float inf = __int_as_float(0x7f800000);
+    const float4* px = reinterpret_cast<const float4*>(tp);
+    const float4* py = reinterpret_cast<const float4*>(tp + TT_LEAF);
+    const float4* pz = reinterpret_cast<const float4*>(tp + 2 * TT_LEAF);
+    const uint64_t qx2 = pk2(x, x), qy2 = pk2(y, y), qz2 = pk2(z, z);
+    float m = inf;
+#pragma unroll
+    for (int g = 0; g < TT_LEAF / 4; ++g) {                  // warp-uniform addresses: one transaction each
+        const float4 X = __ldg(px + g), Y = __ldg(py + g), Z = __ldg(pz + g);
+        float d0, d1, d2, d3;
+        unpk2(s4_d2_x2(qx2, qy2, qz2, pk2(X.x, X.y), pk2(Y.x, Y.y), pk2(Z.x, Z.y)), d0, d1);
+        unpk2(s4_d2_x2(qx2, qy2, qz2, pk2(X.z, X.w), pk2(Y.z, Y.w), pk2(Z.z, Z.w)), d2, d3);
+        m = min3f(m, d0, d1);
+        m = min3f(m, d2, d3);
+    }
+    if (m <= best_d && m < inf) {
+        // this tile holds a vertex at least as near as the best so far: the lowest index among the
+        // vertices at distance exactly m (scalar S4 rounds like the packed form)
+        const uint4* pi = reinterpret_cast<const uint4*>(tp + 3 * TT_LEAF);
+        uint32_t mi = 0xFFFFFFFFu;
+#pragma unroll 2
+        for (int g = 0; g < TT_LEAF / 4; ++g) {
+            const float4 X = __ldg(px + g), Y = __ldg(py + g), Z = __ldg(pz + g);
+            const uint4 I = __ldg(pi + g);
+            mi = (s4_d2(x, y, z, X.x, Y.x, Z.x) == m && I.x < mi) ? I.x : mi;
+            mi = (s4_d2(x, y, z, X.y, Y.y, Z.y) == m && I.y < mi) ? I.y : mi;
+            mi = (s4_d2(x, y, z, X.z, Y.z, Z.z) == m && I.z < mi) ? I.z : mi;
+            mi = (s4_d2(x, y, z, X.w, Y.w, Z.w) == m && I.w < mi) ? I.w : mi;
+        }
+        const unsigned long long k = ((unsigned long long)__float_as_uint(m) << 32) | (unsigned long long)(index_offset + mi);
+        if (k < best) { best = k; best_d = m; }
+    }
+}
+
+// FUSED (one GPU or query-sharded, no percentile): K1 in the prologue (q = imx2 @ (mx1 @ a), warm start
+// from the previous winner) and K3 + K4 (world distance, thresh, target, fp64 moment partials) in the
+// epilogue, like k_nn_bvh_packet<true>.
+template <bool FUSED>
+__global__ void __launch_bounds__(TT_THREADS)
+k_nn_tiletree(const TileTree* __restrict__ tree_ptr, const float* __restrict__ qx, const float* __restrict__ qy,
+              const float* __restrict__ qz, const DevState* __restrict__ st,
+              const float4* __restrict__ mov_slots, const float4* __restrict__ base4, long long base_off,
+              long long n_local, double thresh, int warm, long long n_queries,
+              unsigned long long* __restrict__ keys, uint32_t index_offset, double* __restrict__ partials)
+{
+    if (st->converged) return;
+    __shared__ int s_stack[TT_THREADS / 32][TT_STACK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < n_queries;
+    const float inf = __int_as_float(0x7f800000);
+
+    float x = 0.f, y = 0.f, z = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    unsigned long long best = KEY_NONE;
+    if (active) {
+        if (FUSED) {
+            const float4 a = mov_slots[t];
+            ax = a.x; ay = a.y; az = a.z;
+            float tx, ty, tz;
+            s1_matvec(st->mw_align, ax, ay, az, tx, ty, tz);
+            s1_matvec(st->imx2, tx, ty, tz, x, y, z);
+            if (warm) {
+                const unsigned long long old = keys[t];
+                const long long j = (long long)(uint32_t)(old & 0xFFFFFFFFull) - base_off;
+                if (old != KEY_NONE && j >= 0 && j < n_local) {
+                    const float4 b = base4[j];
+                    const float d = s4_d2(x, y, z, b.x, b.y, b.z);
+                    if (d < inf) best = ((unsigned long long)__float_as_uint(d) << 32) | (old & 0xFFFFFFFFull);
+                }
+            }
+        } else {
+            x = qx[t]; y = qy[t]; z = qz[t];
+            best = keys[t];
+        }
+    }
+    float best_d = (best == KEY_NONE) ? inf : __uint_as_float((uint32_t)(best >> 32));
+    const TileTree& tree = *tree_ptr;
+    const int top = tree.n_levels - 1;
+
+    if (tree.n_levels > 0) {
+        // ---- no bound yet on some lane: greedy descent to the tile nearest the warp's first query --------
+        if (__any_sync(0xffffffffu, active && !(best_d < inf))) {
+            const int src = __ffs(__ballot_sync(0xffffffffu, active)) - 1;      // >= 0: some lane is active here
+            const float sx = __shfl_sync(0xffffffffu, x, src), sy = __shfl_sync(0xffffffffu, y, src),
+                        sz = __shfl_sync(0xffffffffu, z, src);
+            int group = 0;
+            for (int lvl = top; lvl >= 0; --lvl) {
+                const int c = group * TT_FAN + lane;
+                float d = inf;
+                if (c < tree.count[lvl]) {
+                    const float4 lo = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c));
+                    const float4 hi = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c) + 1);
+                    d = box_lower_bound(sx, sy, sz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+                    if (!(d >= 0.0f)) d = inf;                                  // NaN query: any non-empty box will do
+                    if (lo.x > hi.x) d = inf; else d = fminf(d, 3.0e38f);       // empty box never, a real one always finite
+                }
+                const uint32_t dm = __reduce_min_sync(0xffffffffu, __float_as_uint(d));
+                const unsigned who = __ballot_sync(0xffffffffu, __float_as_uint(d) == dm);
+                group = group * TT_FAN + (__ffs(who) - 1);
+            }
+            if (group < tree.count[0])
+                tt_scan_tile(tree.tiles + (size_t)group * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
+        }
+
+        // ---- walk: groups of 32 boxes against the warp's patch box, one box per lane -------------------
+        int sp = 0;
+        if (lane == 0) s_stack[warp][0] = top << 26;            // entry = level << 26 | group
+        sp = 1;
+        __syncwarp();
+        float plo[3], phi[3];
+        bool patch_stale = true;
+        while (sp > 0) {
+            if (patch_stale) {
+                // the ball of a lane: radius sqrt(best_d) (1 + 2e-6) + the rounding of q -+ r itself
+                const float r = active ? sqrtf(best_d) * TT_GROW : 0.0f;
+                const float q[3] = {x, y, z};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float pad = fabsf(q[k]) * 2.4e-7f;
+                    plo[k] = tt_warp_min(active ? (q[k] - r) - pad : inf);
+                    phi[k] = tt_warp_max(active ? (q[k] + r) + pad : -inf);
+                }
+                patch_stale = false;
+            }
+            --sp;
+            const int e = s_stack[warp][sp];
+            __syncwarp();
+            const int lvl = e >> 26, group = e & 0x3FFFFFF;
+            const int c = group * TT_FAN + lane;
+            bool hit = false;
+            if (c < tree.count[lvl]) {
+                const float4 lo = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c));
+                const float4 hi = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c) + 1);
+                // NaN anywhere (a NaN query poisons the patch box) counts as a hit: nothing is skipped
+                hit = !(lo.x > phi[0] || hi.x < plo[0] || lo.y > phi[1] || hi.y < plo[1] || lo.z > phi[2] || hi.z < plo[2]);
+                if (lo.x > hi.x) hit = false;                                   // empty box
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (lvl > 0) {
+                // push the hit groups, lowest child last so that it is popped first
+                const int n_hit = __popc(mask);
+                if (hit) {
+                    const int pos = sp + n_hit - 1 - __popc(mask & ((1u << lane) - 1u));
+                    if (pos < TT_STACK) s_stack[warp][pos] = ((lvl - 1) << 26) | c;
+                }
+                sp = min(sp + n_hit, TT_STACK);
+                __syncwarp();
+            } else {
+                bool improved = false;
+                while (mask) {
+                    const int child = group * TT_FAN + (__ffs(mask) - 1);
+                    mask &= mask - 1;
+                    const float before = best_d;
+                    tt_scan_tile(tree.tiles + (size_t)child * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
+                    improved = improved || (best_d < before);
+                }
+                patch_stale = __any_sync(0xffffffffu, improved);
+            }
+        }
+    }
+    if (active) keys[t] = best;
+    if (FUSED) {
+        // K3 + K4 for this thread's query (functions/general.py:299-306, :160-181)
+        bool keep = false;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        double dist = 0.0;
+        if (active && best != KEY_NONE) {
+            const float4 w = base4[(long long)(uint32_t)(best & 0xFFFFFFFFull) - base_off];   // the winner
+            float wqx, wqy, wqz, w1x, w1y, w1z;
+            s1_matvec(st->mw_base, x, y, z, wqx, wqy, wqz);
+            s1_matvec(st->mw_base, w.x, w.y, w.z, w1x, w1y, w1z);
+            dist = s5_length(__fsub_rn(wqx, w1x), __fsub_rn(wqy, w1y), __fsub_rn(wqz, w1z));
+            if (dist < thresh) {
+                s1_matvec(st->imx1, w1x, w1y, w1z, bx, by, bz);
+                keep = true;
+            }
+        }
+        fused_pair_moments<TT_THREADS>(keep, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2], partials);
+    }
+}
+
+}  // namespace icp

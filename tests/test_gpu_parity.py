@@ -213,25 +213,32 @@ def _clouds_for_bvh(case):
     raise KeyError(case)
 
 
+TREE_VARIANTS = [0, 12, 10]      # tile-tree warp walk (default), LBVH packet walk, LBVH per-thread walk
+
+
+@pytest.mark.parametrize("variant", TREE_VARIANTS)
 @pytest.mark.parametrize("case", ["surface", "far_outliers", "duplicates", "collinear", "volume", "lattice"])
-def test_bvh_matches_bruteforce_oracle(case):
+def test_bvh_matches_bruteforce_oracle(case, variant):
     base, mov = _clouds_for_bvh(case)
-    with IcpEngine(nn_mode=1) as e:
+    with IcpEngine(nn_mode=1, nn_variant=variant) as e:
         e.set_base(base)
         e.set_moving(mov)
         e.set_matrices(np.eye(4), np.eye(4))
         idx, d2 = e.nn()
+        idx2, d22 = e.nn()                   # warm-started with the exact answer: ties must survive
     oi, od = orc.nn_bruteforce(mov, base)
-    assert np.array_equal(idx, oi)
+    assert np.array_equal(idx, oi) and np.array_equal(idx2, oi)
     assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(d22.view(np.uint32), od.view(np.uint32))
 
 
 @pytest.mark.parametrize("n_base,n_mov", [(1, 1), (1, 300), (7, 9), (8, 8), (9, 100), (1023, 1),
-                                          (1025, 1025), (4097, 2049)])
-def test_bvh_ragged_sizes(n_base, n_mov):
+                                          (1025, 1025), (4097, 2049), (33, 70), (1056, 31), (40000, 5)])
+@pytest.mark.parametrize("variant", [0, 12])
+def test_bvh_ragged_sizes(n_base, n_mov, variant):
     base = _rand_cloud(n_base, 10 + n_base)
     mov = _rand_cloud(n_mov, 20 + n_mov)
-    with IcpEngine(nn_mode=1) as e:
+    with IcpEngine(nn_mode=1, nn_variant=variant) as e:
         e.set_base(base)
         e.set_moving(mov)
         e.set_matrices(np.eye(4), np.eye(4))
@@ -401,11 +408,12 @@ def test_stepwise_parity_against_oracle(name):
             np.testing.assert_array_equal(e.matrix_world(), ms.matmul44(mw, M.astype(np.float32)))
 
 
-def test_bvh_warm_start_stays_exact_over_iterations():
+@pytest.mark.parametrize("variant", [0, 12])
+def test_bvh_warm_start_stays_exact_over_iterations(variant):
     """BVH mode re-uses last iteration's winner as the initial bound; every iteration's keys must
     still equal the brute-force oracle evaluated at the engine's own current pose."""
     cfg = meshgen.config_cloud(50_000, 80_000, 71, 72)
-    with IcpEngine(thresh=0.5, use_target=False, nn_mode=1) as e:
+    with IcpEngine(thresh=0.5, use_target=False, nn_mode=1, nn_variant=variant) as e:
         e.set_base(cfg["base"])
         e.set_moving(cfg["moving"])
         e.set_matrices(np.eye(4), np.eye(4))
