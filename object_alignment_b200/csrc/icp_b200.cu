@@ -493,11 +493,22 @@ __device__ inline double rotation_angle_of(const float* nm)
 }
 
 // K5: solve, pose update (icp_align.py:116-121), record, convergence ring (icp_align.py:136-142)
+__device__ void solve_update_body(DevState* st, const double* __restrict__ moments, int scale_mode,
+                                  int use_target, double target_d, icp_iter_stats* __restrict__ stats,
+                                  int stats_capacity);
+
 __global__ void k_solve_update(DevState* st, const double* __restrict__ moments, int scale_mode,
                                int use_target, double target_d, icp_iter_stats* __restrict__ stats,
                                int stats_capacity)
 {
     if (threadIdx.x != 0 || st->converged) return;
+    solve_update_body(st, moments, scale_mode, use_target, target_d, stats, stats_capacity);
+}
+
+__device__ void solve_update_body(DevState* st, const double* __restrict__ moments, int scale_mode,
+                                  int use_target, double target_d, icp_iter_stats* __restrict__ stats,
+                                  int stats_capacity)
+{
     double M[16], mean_d, std_d;
     if (!solve_from_moments(moments, st->shift, scale_mode, M, &mean_d, &std_d)) {
         st->error = ICP_ERR_TOO_FEW_PAIRS;
@@ -525,6 +536,31 @@ __global__ void k_solve_update(DevState* st, const double* __restrict__ moments,
         if (all) st->converged = 1;
     }
     st->n_iter = n + 1;
+    // the next iteration's mx1.inverted() (general.py:265): mw_base has not changed, so imx2 stands
+    if (!s2_invert(st->mw_align, st->imx1)) {
+        st->error = ICP_ERR_SINGULAR;
+        st->converged = 1;
+    }
+}
+
+// Single-GPU tail of an iteration in ONE launch: fixed-order sum of the per-CTA moment partials (one
+// warp per component), then the solve + pose update by thread 0.
+__global__ void __launch_bounds__(MOM * 32)
+k_reduce_solve(DevState* st, const double* __restrict__ partials, int n_partials, double* __restrict__ moments,
+               int scale_mode, int use_target, double target_d, icp_iter_stats* __restrict__ stats, int stats_capacity);
+
+__global__ void __launch_bounds__(MOM * 32)
+k_reduce_solve(DevState* st, const double* __restrict__ partials, int n_partials, double* __restrict__ moments,
+               int scale_mode, int use_target, double target_d, icp_iter_stats* __restrict__ stats, int stats_capacity)
+{
+    if (st->converged) return;
+    const int lane = threadIdx.x & 31, comp = threadIdx.x >> 5;
+    double v = 0.0;
+    for (int i = lane; i < n_partials; i += 32) v += partials[(size_t)i * MOM + comp];
+    v = warp_sum(v);
+    if (lane == 0) moments[comp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) solve_update_body(st, moments, scale_mode, use_target, target_d, stats, stats_capacity);
 }
 
 // solve only (affine_matrix_from_points entry point): no pose update
@@ -809,6 +845,7 @@ struct icp_handle {
     int* d_vlist = nullptr;
     long long vlist_capacity = 0, n_vlist = 0;
     bool has_vlist = false, have_moving = false, have_matrices = false;
+    bool pose_dirty = true;               // imx1 / imx2 on the device are older than the matrices (k_prepare_pose needed)
     std::vector<int32_t> h_vlist;         // host copy of the uploaded vertex list (to recognise a repeated upload)
     // queries
     float* d_q = nullptr;                 // 3 planes of q_capacity
@@ -1643,14 +1680,18 @@ int enqueue_nn(icp_handle* h, long long n_q)
     }
     {
         ProfScope ps(h, 3);
-        k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
+        if (h->pose_dirty) {          // k_solve_update keeps imx1 current between iterations
+            k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
+            h->launches += 1;
+            h->pose_dirty = false;
+        }
         if (n_q > 0)
             k_transform_queries<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(
                 h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q,
                 slots ? h->d_slot_pos : nullptr, qx, qy, qz, h->d_keys,
                 warm_src, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off,
                 h->n_local, h->bound_active ? h->d_keys : nullptr, h->bound_active ? h->d_bound : nullptr);
-        h->launches += 2;
+        h->launches += 1;
     }
     if (h->surface != (h->prm.nn_mode == ICP_NN_SURFACE))
         return fail(h, ICP_ERR_STATE, "nn_mode ICP_NN_SURFACE needs icp_set_base_triangles (and the vertex modes need icp_set_base)");
@@ -1760,10 +1801,11 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     const int g = (int)std::max<long long>(1, (n_q + cta - 1) / cta);
     rc = ensure_partials(h, g);
     if (rc) return rc;
-    {
+    if (h->pose_dirty) {
         ProfScope ps(h, 3);
         k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
         h->launches += 1;
+        h->pose_dirty = false;
     }
     {
         ProfScope ps(h, 0);
@@ -1791,6 +1833,14 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     }
     h->warm_valid = true;
     h->bf_warm_valid = false;
+    if (h->prm.world_size == 1 && g <= 16384) {      // one launch: reduce + solve + pose update
+        ProfScope ps(h, 2);
+        k_reduce_solve<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments, h->prm.align_meth == 1,
+                                                      h->prm.use_target, h->prm.target_d, h->d_stats, h->stats_capacity);
+        h->launches += 1;
+        CUDA_TRY(h, cudaGetLastError());
+        return ICP_OK;
+    }
     {
         ProfScope ps(h, 2);
         rc = launch_reduce(h, h->d_state, g);
@@ -1831,8 +1881,16 @@ int enqueue_iteration(icp_handle* h, long long n_q)
             h->d_keys, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off, h->n_local, h->prm.thresh,
             h->prm.reject_fraction > 0 ? 1 : 0,
             uses_slots(h) ? h->d_slot_pos : nullptr, uses_slots(h) ? h->d_mov_slots : nullptr, h->d_partials);
+        h->launches += 1;
+        if (h->prm.world_size == 1) {
+            k_reduce_solve<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments, h->prm.align_meth == 1,
+                                                          h->prm.use_target, h->prm.target_d, h->d_stats, h->stats_capacity);
+            h->launches += 1;
+            CUDA_TRY(h, cudaGetLastError());
+            return ICP_OK;
+        }
         k_reduce_moments<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments);
-        h->launches += 2;
+        h->launches += 1;
     }
     if (h->prm.world_size > 1) {
         ProfScope ps(h, 4);
@@ -1920,6 +1978,7 @@ int clear_device_error(icp_handle* h)
     int rc = read_state(h, &st);
     if (rc) return rc;
     if (st.error) {
+        h->pose_dirty = true;
         st.error = 0;
         st.converged = 0;
         CUDA_TRY(h, cudaMemcpyAsync(h->d_state, &st, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
@@ -2218,6 +2277,7 @@ int icp_set_matrices(icp_handle* h, const float mw_align[16], const float mw_bas
     CUDA_TRY(h, cudaMemcpyAsync(h->d_state, both, sizeof(both), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_matrices = true;
+    h->pose_dirty = true;
     return ICP_OK;
 }
 

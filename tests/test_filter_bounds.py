@@ -118,3 +118,119 @@ def test_margin_is_not_vacuous():
     # slack is reported relative to (|q'|^2 + B^2); subtracting the 4e-6 the kernels add shows what
     # the raw rounding error alone would do
     assert min(m.values()) - 4.0e-6 < 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# q16 kernel (csrc/nn_bruteforce_q16.cuh): 16-bit quantised interval test.  Property: for every query q
+# and EVERY vertex j of a tile with best = S4(q, b_j) (j ties the running best), j's quantised
+# coordinate lies inside the query's integer interval on all three axes -- for the alu-only loop
+# (exact per-half wrap-around) and for the split loop (plain 32-bit add: a carry out of the low half
+# may raise the high half by one, the width is one step larger).
+# ------------------------------------------------------------------------------------------------
+Q16_LEVELS = F(65534.0)
+
+
+def q16_build(pts):
+    """k_build_q16_tiles: per-axis lower corner, steps per unit (fp32), u = round((p - lo) * inv) in double."""
+    lo, hi = pts.min(axis=0), pts.max(axis=0)
+    ext = (hi - lo).astype(F)
+    ext = np.maximum(ext, np.maximum(np.maximum(np.abs(lo), np.abs(hi)) * F(1.0e-6), F(1.0e-30))).astype(F)
+    inv = (Q16_LEVELS / ext).astype(F)
+    t = (pts.astype(np.float64) - lo.astype(np.float64)) * inv.astype(np.float64)
+    u = np.clip(np.floor(t + 0.5), 0.0, 65534.0).astype(np.int64)
+    return lo, inv, u
+
+
+def q16_setup(q, T, lo, inv, carry):
+    """q16_setup<CARRY>: (li, W) per query with the kernel's fp32 operation order; W = 0 means "never"."""
+    c = ((q - lo).astype(F) * inv).astype(F)
+    r = (T * inv).astype(F)
+    e = fma(np.full_like(c, F(4.8e-7)), (np.abs(c) + np.abs(r)).astype(F), np.full_like(c, F(2.0)))
+    lf = ((c - r).astype(F) - e).astype(F)
+    hf = ((c + r).astype(F) + e).astype(F)
+    never = (hf < 0) | (lf > Q16_LEVELS) | (T < 0)
+    li = np.floor(np.clip(lf, 0.0, 65534.0)).astype(np.int64)
+    hi = np.ceil(np.clip(hf, 0.0, 65534.0)).astype(np.int64)
+    W = hi - li + 1 + ((li > 0) & carry)
+    return li, np.where(never, 0, W)
+
+
+def q16_hit(u_lo_half, u_hi_half, li, W, carry):
+    """The hot loop's test on one word (two vertices): per half (x + (65536 - li)) mod 2^16 < W; with
+    `carry` the two halves are added as ONE 32-bit integer (IMAD), so the low half's carry enters the high."""
+    nlo = (65536 - li) & 0xFFFF
+    if not carry:
+        return ((u_lo_half + nlo) & 0xFFFF) < W, ((u_hi_half + nlo) & 0xFFFF) < W
+    word = (u_lo_half | (u_hi_half << 16)) + (nlo | (nlo << 16))
+    return (word & 0xFFFF) < W, ((word >> 16) & 0xFFFF) < W
+
+
+@pytest.mark.parametrize("carry", [False, True])
+@pytest.mark.parametrize("kind", ["blob", "flat", "needle", "lattice"])
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1.0, 800.0), (1e-4, 0.0), (1e-4, 0.3), (1e3, -5e4)])
+def test_q16_interval_never_misses_a_vertex_that_ties_the_best(kind, scale, offset, carry):
+    rng = np.random.default_rng(zlib.crc32(repr(("q16", kind, scale, offset)).encode()))
+    pts = _tile(rng, kind, scale, np.array([offset, -0.6 * offset, 0.3 * offset]))
+    cen = pts.mean(axis=0)
+    ext = float(np.abs(pts - cen).max())
+    q = np.concatenate([
+        pts[rng.integers(0, len(pts), 48)],
+        pts[rng.integers(0, len(pts), 48)] + rng.standard_normal((48, 3)) * 0.01 * ext,
+        cen + rng.standard_normal((48, 3)) * ext,
+        cen + rng.standard_normal((48, 3)) * 30 * ext,
+    ]).astype(F)
+    lo, inv, u = q16_build(pts)
+    nq, nv = q.shape[0], pts.shape[0]
+    best = s4_d2(np.broadcast_to(q[:, None, :], (nq, nv, 3)), np.broadcast_to(pts[None], (nq, nv, 3)))
+    T = (np.sqrt(best).astype(F) * F(1.000001)).astype(F)              # q16_radius
+    neighbour = np.roll(u, 1, axis=0)                                   # the other vertex of the same word
+    for axis in range(3):
+        li, W = q16_setup(q[:, None, axis], T, lo[axis], inv[axis], carry)
+        assert (W > 0).all(), "a vertex at distance `best` made its own tile unreachable"
+        # j in the low half of a word (any neighbour above it), and j in the high half (the low half's
+        # carry may or may not arrive: try the neighbour that carries and the one that does not)
+        hit_low, _ = q16_hit(u[None, :, axis], neighbour[None, :, axis], li, W, carry)
+        assert hit_low.all()
+        for other in (neighbour[None, :, axis], np.zeros_like(u[None, :, axis]), np.full_like(u[None, :, axis], 65534)):
+            _, hit_high = q16_hit(np.broadcast_to(other, li.shape), u[None, :, axis], li, W, carry)
+            assert hit_high.all()
+        # padding (u = 65535, the high half of a ragged tile's last words) must not be needed for
+        # correctness; it may only cost a false positive, which the exact metric rejects (coordinates +inf)
+
+
+def test_q16_filter_actually_prunes():
+    """Not vacuous: far vertices are outside the interval, and a radius that is too small loses vertices."""
+    rng = np.random.default_rng(9)
+    pts = _tile(rng, "flat", 1.0, np.zeros(3))
+    lo, inv, u = q16_build(pts)
+    q = pts[:64] + F(1e-3)
+    best = s4_d2(q, pts[:64])
+    T = (np.sqrt(best).astype(F) * F(1.000001)).astype(F)
+    li, W = q16_setup(q[:, None, 0], T[:, None], lo[0], inv[0], False)
+    inside = ((u[None, :, 0] - li) % 65536) < W
+    assert inside.mean() < 0.2                                          # most of the tile is pruned along x alone
+    li, W = q16_setup(q[:, None, 0], (T * F(0.5))[:, None], lo[0], inv[0], False)
+    own = ((u[None, :64, 0] - li) % 65536) < W
+    assert not np.diagonal(own).all()                                   # half the radius drops true neighbours
+
+
+def test_global_pruning_bound_is_valid():
+    """k_transform_queries' bound for base-sharded runs: the previous pass's GLOBAL winner v of a slot lies
+    within sqrt(d_old) + |q_new - q_old| of the new query, so the new winner's S4 distance never exceeds
+    (sqrt(d_old) + |q_new - q_old|)^2 (1 + 4e-6) -- whatever moved the query."""
+    rng = np.random.default_rng(17)
+    base = (rng.standard_normal((4000, 3)) * 0.5).astype(F)
+    q_old = (rng.standard_normal((3000, 3)) * 0.5).astype(F)
+    d_all = s4_d2(np.broadcast_to(q_old[:, None, :], (3000, 4000, 3)), np.broadcast_to(base[None], (3000, 4000, 3)))
+    win = d_all.argmin(axis=1)
+    d_old = d_all[np.arange(3000), win]
+    for jump in (1e-4, 1e-2, 1.0):
+        q_new = (q_old + rng.standard_normal((3000, 3)) * jump).astype(F)
+        e = (q_new - q_old).astype(F)
+        dq = np.sqrt(fma(e[:, 2], e[:, 2], fma(e[:, 1], e[:, 1], (e[:, 0] * e[:, 0]).astype(F)))).astype(F)
+        sr = (np.sqrt(d_old).astype(F) + dq).astype(F)
+        bound = ((sr * sr).astype(F) * F(1.000004)).astype(F)
+        d_new_same_vertex = s4_d2(q_new, base[win])
+        assert (d_new_same_vertex <= bound).all()
+        d_new_all = s4_d2(np.broadcast_to(q_new[:, None, :], (3000, 4000, 3)), np.broadcast_to(base[None], (3000, 4000, 3)))
+        assert (d_new_all.min(axis=1) <= bound).all()
