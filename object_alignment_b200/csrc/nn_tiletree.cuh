@@ -259,24 +259,43 @@ k_nn_tiletree(const TileTree* __restrict__ tree_ptr, const float* __restrict__ q
                 if (lo.x > hi.x) hit = false;                                   // empty box
             }
             unsigned mask = __ballot_sync(0xffffffffu, hit);
+            // The patch box is only a summary (32 consecutive Morton slots can straddle a jump of the curve
+            // and span half the object): every candidate box is re-tested against each lane's OWN ball,
+            // lane = query, before anything is pushed or scanned (~20 instructions per candidate).
+            float4 clo = make_float4(0.f, 0.f, 0.f, 0.f), chi = clo;
+            if (hit) {
+                clo = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c));
+                chi = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c) + 1);
+            }
+            unsigned keep = 0u;
+            bool improved = false;
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float lx = __shfl_sync(0xffffffffu, clo.x, b), ly = __shfl_sync(0xffffffffu, clo.y, b),
+                            lz = __shfl_sync(0xffffffffu, clo.z, b), hx = __shfl_sync(0xffffffffu, chi.x, b),
+                            hy = __shfl_sync(0xffffffffu, chi.y, b), hz = __shfl_sync(0xffffffffu, chi.z, b);
+                const float d = box_lower_bound(x, y, z, lx, ly, lz, hx, hy, hz);
+                // same prune rule as nn_bvh.cuh: skip only when the shrunk bound is STRICTLY greater
+                if (!__any_sync(0xffffffffu, active && !(d * BVH_SHRINK > best_d))) continue;
+                if (lvl > 0) {
+                    keep |= 1u << b;
+                } else {                                 // a leaf tile some lane needs: scan it now, with the bounds as they are
+                    const float before = best_d;
+                    tt_scan_tile(tree.tiles + (size_t)(group * TT_FAN + b) * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
+                    improved = improved || (best_d < before);
+                }
+            }
             if (lvl > 0) {
-                // push the hit groups, lowest child last so that it is popped first
-                const int n_hit = __popc(mask);
-                if (hit) {
-                    const int pos = sp + n_hit - 1 - __popc(mask & ((1u << lane) - 1u));
+                // push the surviving groups, lowest child last so that it is popped first
+                const int n_hit = __popc(keep);
+                if ((keep >> lane) & 1u) {
+                    const int pos = sp + n_hit - 1 - __popc(keep & ((1u << lane) - 1u));
                     if (pos < TT_STACK) s_stack[warp][pos] = ((lvl - 1) << 26) | c;
                 }
                 sp = min(sp + n_hit, TT_STACK);
                 __syncwarp();
             } else {
-                bool improved = false;
-                while (mask) {
-                    const int child = group * TT_FAN + (__ffs(mask) - 1);
-                    mask &= mask - 1;
-                    const float before = best_d;
-                    tt_scan_tile(tree.tiles + (size_t)child * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
-                    improved = improved || (best_d < before);
-                }
                 patch_stale = __any_sync(0xffffffffu, improved);
             }
         }
