@@ -955,7 +955,7 @@ bool uses_slots(const icp_handle* h)
 {
     if (h->prm.nn_mode != ICP_NN_BRUTEFORCE) return true;
     const int v = h->prm.nn_variant;
-    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36) || slab_variant(v) || (v >= 50 && v <= 69);
+    return v == 0 || v == 30 || v == 31 || (v >= 34 && v <= 36) || slab_variant(v) || (v >= 50 && v <= 79);
 }
 
 long long query_count(const icp_handle* h)
@@ -1334,13 +1334,31 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
     return ICP_OK;
 }
 
-bool q16_variant(int v) { return v >= 50 && v <= 69; }   // 58 = 62 without the global pruning bound (A/B)
+bool q16_variant(int v) { return v >= 50 && v <= 79; }   // 58 = 62 without the global pruning bound (A/B)
+
+int build_tiletree(icp_handle* h);
 
 int launch_nn(icp_handle* h, long long n_q)
 {
     if (n_q <= 0 || h->n_tiles <= 0) return ICP_OK;
     int variant = h->prm.nn_variant;
-    if (q16_variant(variant) && !h->bf_warm_active) variant = 0;       // the q16 kernel needs a seed: cold pass below
+    // The q16 kernel needs a seed.  First pass of the default path: every query takes the nearest vertex
+    // of the Morton tile nearest to it (greedy descent of the tile tree, 0.1 ms) as its seed -- a real
+    // vertex, so the exhaustive seeded pass that follows is exact whatever the seed's quality.
+    // nn_variant 59: first pass by the unseeded expansion-filter kernel instead (round-1 behaviour).
+    if ((variant == 0 || (q16_variant(variant) && variant != 59)) && !h->bf_warm_active && h->n_tiles >= 16) {
+        int rc = build_tiletree(h);
+        if (rc) return rc;
+        ProfScope ps(h, 3);
+        float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+        k_tt_seed<<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_tt_desc, qx, qy, qz, n_q, h->d_keys,
+                                                                        (uint32_t)h->base_off, &h->d_state->converged);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        h->bf_warm_active = true;
+    }
+    if (q16_variant(variant) && !h->bf_warm_active) variant = 0;       // no seed (tiny shard / variant 59): cold pass below
+    if (variant == 59) variant = 62;
     if (variant == 0) {
         if (h->bf_warm_active && h->n_tiles >= 16) variant = 62;       // seeded: 16-bit slab kernel
         else variant = h->n_tiles >= 256 ? 20 : 2;                     // cold: filter / direct kernel
@@ -1383,6 +1401,10 @@ int launch_nn(icp_handle* h, long long n_q)
         case 64: return launch_nn_q16_t<4, 4, 64, 1, 3>(h, n_q);
         case 65: return launch_nn_q16_t<4, 4, 64, 2, 3>(h, n_q);
         case 67: return launch_nn_q16_t<4, 4, 64, 3, 3>(h, n_q);
+        case 70: return launch_nn_q16_t<4, 4, 128, 5, 3>(h, n_q);      // one third VIADDMNMX, two thirds IMAD + VIMNMX3
+        case 71: return launch_nn_q16_t<4, 8, 128, 3, 3>(h, n_q);      // 62 with an 8-tile ring
+        case 72: return launch_nn_q16_t<4, 8, 128, 5, 3>(h, n_q);      // 70 with an 8-tile ring
+        case 73: return launch_nn_q16_t<4, 8, 256, 5, 3>(h, n_q);      // 72 with 256-vertex chunks
         case 68: return launch_nn_q16_t<8, 4, 128, 3>(h, n_q);
         case 69: return launch_nn_q16_t<2, 4, 128, 3, 3>(h, n_q);
         case 40: return launch_nn_slab_t<4, 3, 32>(h, n_q);

@@ -72,32 +72,60 @@ __device__ __forceinline__ void block_reduce_moments(const double* acc, double* 
     }
 }
 
+// Sum over the warp of 8 per-lane values at once: recursive halving (4 + 2 + 1 adds) leaves lane l with the
+// total of component (l & 7) over its group of 8 lanes, two butterfly steps finish it across the 4 groups.
+// 9 fp64 adds and 9 64-bit shuffles for 8 components, against 40 + 40 for eight separate butterflies --
+// fp64 adds are the expensive instruction here (ncu: the 100-DADD epilogue was 19 % of the fused
+// tile-tree kernel's samples).  The order of the additions is fixed, so the result is deterministic.
+__device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane)
+{
+    double a[4], b[2];
+    const bool u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = u4 ? v[i] : v[i + 4], keep = u4 ? v[i + 4] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = u2 ? a[i] : a[i + 2], keep = u2 ? a[i + 2] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    double r = (u1 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, u1 ? b[0] : b[1], 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    return r;                                   // component ((lane & 4) | (lane & 2) | (lane & 1)) == lane & 7
+}
+
 // Epilogue of the fused search kernels: one kept pair (or none) per thread -> partials[blockIdx.x][MOM].
-// Each moment is formed and warp-summed on the spot instead of living in a 20-double per-thread
-// accumulator, so the fp64 vector does not set the register count (and the occupancy) of the walk.
+// The 20 moments are formed and warp-summed eight at a time, so the fp64 vector never sets the register
+// count (and the occupancy) of the walk.
 template <int THREADS>
 __device__ __forceinline__ void fused_pair_moments(bool keep, float ax, float ay, float az, float bx, float by,
                                                    float bz, double dist, double s0, double s1, double s2,
                                                    double* __restrict__ partials)
 {
-    __shared__ double sh[THREADS / 32][MOM];
+    __shared__ double sh[THREADS / 32][24];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double k = keep ? 1.0 : 0.0;
     const double a0 = keep ? (double)ax - s0 : 0.0, a1 = keep ? (double)ay - s1 : 0.0, a2 = keep ? (double)az - s2 : 0.0;
     const double b0 = keep ? (double)bx - s0 : 0.0, b1 = keep ? (double)by - s1 : 0.0, b2 = keep ? (double)bz - s2 : 0.0;
     const double d = keep ? dist : 0.0;
-#define ICP_MOM_TERM(i, expr) { const double v_ = warp_sum(expr); if (lane == 0) sh[warp][i] = v_; }
-    ICP_MOM_TERM(0, k)
-    ICP_MOM_TERM(1, a0) ICP_MOM_TERM(2, a1) ICP_MOM_TERM(3, a2)
-    ICP_MOM_TERM(4, b0) ICP_MOM_TERM(5, b1) ICP_MOM_TERM(6, b2)
-    ICP_MOM_TERM(7, b0 * a0) ICP_MOM_TERM(8, b0 * a1) ICP_MOM_TERM(9, b0 * a2)
-    ICP_MOM_TERM(10, b1 * a0) ICP_MOM_TERM(11, b1 * a1) ICP_MOM_TERM(12, b1 * a2)
-    ICP_MOM_TERM(13, b2 * a0) ICP_MOM_TERM(14, b2 * a1) ICP_MOM_TERM(15, b2 * a2)
-    ICP_MOM_TERM(16, a0 * a0 + a1 * a1 + a2 * a2)
-    ICP_MOM_TERM(17, b0 * b0 + b1 * b1 + b2 * b2)
-    ICP_MOM_TERM(18, d)
-    ICP_MOM_TERM(19, d * d)
-#undef ICP_MOM_TERM
+    {
+        const double v[8] = {k, a0, a1, a2, b0, b1, b2, b0 * a0};                       // moments 0..7
+        const double r = warp_sum8(v, lane);
+        if (lane < 8) sh[warp][lane] = r;
+    }
+    {
+        const double v[8] = {b0 * a1, b0 * a2, b1 * a0, b1 * a1, b1 * a2, b2 * a0, b2 * a1, b2 * a2};   // 8..15
+        const double r = warp_sum8(v, lane);
+        if (lane < 8) sh[warp][8 + lane] = r;
+    }
+    {
+        const double v[8] = {a0 * a0 + a1 * a1 + a2 * a2, b0 * b0 + b1 * b1 + b2 * b2, d, d * d, 0.0, 0.0, 0.0, 0.0};   // 16..19
+        const double r = warp_sum8(v, lane);
+        if (lane < 8) sh[warp][16 + lane] = r;
+    }
     __syncthreads();
     if (threadIdx.x < MOM) {
         double v = 0.0;

@@ -365,6 +365,37 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
             uint32_t acc[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] = wp[r];
+            if (MIX == 5) {
+                // every third word by VIADDMNMX, the other two by IMAD + IMAD + VIMNMX3: alu and fma pipes both
+                // at 4 cycles per 6 vertices (0.667 per pair), 4 issue slots per 6 vertices
+                uint32_t pend[R];
+                int n_pend = 0;
+#pragma unroll
+                for (int g = 0; g < CH / 8; ++g) {
+                    const uint4 v = plane[c * (CH / 8) + g];
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int wi = 4 * g + k;                 // compile-time after unrolling
+                        if (wi % 3 == 0) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) acc[r] = __viaddmin_u16x2(w4[k], nlo[r], acc[r]);
+                        } else if (n_pend == 0) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) pend[r] = imad_add(w4[k], one, nlo[r]);
+                            n_pend = 1;
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) acc[r] = __vimin3_u16x2(acc[r], pend[r], imad_add(w4[k], one, nlo[r]));
+                            n_pend = 0;
+                        }
+                    }
+                }
+                if (n_pend) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = __vminu2(acc[r], pend[r]);
+                }
+            } else
 #pragma unroll
             for (int g = 0; g < CH / 8; ++g) {
                 const uint4 v = plane[c * (CH / 8) + g];

@@ -117,6 +117,31 @@ __device__ __forceinline__ float tt_warp_max(float v) { return tt_o2f(__reduce_m
 
 constexpr float TT_GROW = 1.000002f;   // 2e-6 relative on the radius: > the fp32 rounding of S4 (5 ulp) and of the box tests
 
+// lowest index among the vertices of a tile at S4 distance exactly m, looking only at the runs of 8 vertices
+// named by `runs` (out of line: keeps the scan's 24 vector loads from staying live; scalar S4 rounds
+// like the packed form)
+__device__ __noinline__ uint32_t tt_lowest_index_at(const float* __restrict__ tp, float x, float y, float z, float m, int runs)
+{
+    const float4* px = reinterpret_cast<const float4*>(tp);
+    const float4* py = reinterpret_cast<const float4*>(tp + TT_LEAF);
+    const float4* pz = reinterpret_cast<const float4*>(tp + 2 * TT_LEAF);
+    const uint4* pi = reinterpret_cast<const uint4*>(tp + 3 * TT_LEAF);
+    uint32_t mi = 0xFFFFFFFFu;
+    for (int h = 0; h < TT_LEAF / 8; ++h) {
+        if (!((runs >> h) & 1)) continue;
+#pragma unroll
+        for (int g = 2 * h; g < 2 * h + 2; ++g) {
+            const float4 X = __ldg(px + g), Y = __ldg(py + g), Z = __ldg(pz + g);
+            const uint4 I = __ldg(pi + g);
+            mi = (s4_d2(x, y, z, X.x, Y.x, Z.x) == m && I.x < mi) ? I.x : mi;
+            mi = (s4_d2(x, y, z, X.y, Y.y, Z.y) == m && I.y < mi) ? I.y : mi;
+            mi = (s4_d2(x, y, z, X.z, Y.z, Z.z) == m && I.z < mi) ? I.z : mi;
+            mi = (s4_d2(x, y, z, X.w, Y.w, Z.w) == m && I.w < mi) ? I.w : mi;
+        }
+    }
+    return mi;
+}
+
 // Scan one leaf tile for this lane's query: running minimum with packed math, exact key on demand.
 __device__ __forceinline__ void tt_scan_tile(const float* __restrict__ tp, float x, float y, float z,
                                              uint32_t index_offset, unsigned long long& best, float& best_d)
@@ -126,33 +151,64 @@ __device__ __forceinline__ void tt_scan_tile(const float* __restrict__ tp, float
     const float4* py = reinterpret_cast<const float4*>(tp + TT_LEAF);
     const float4* pz = reinterpret_cast<const float4*>(tp + 2 * TT_LEAF);
     const uint64_t qx2 = pk2(x, x), qy2 = pk2(y, y), qz2 = pk2(z, z);
-    float m = inf;
+    float mg[TT_LEAF / 8];                                   // minimum per run of 8 vertices
 #pragma unroll
     for (int g = 0; g < TT_LEAF / 4; ++g) {                  // warp-uniform addresses: one transaction each
         const float4 X = __ldg(px + g), Y = __ldg(py + g), Z = __ldg(pz + g);
         float d0, d1, d2, d3;
         unpk2(s4_d2_x2(qx2, qy2, qz2, pk2(X.x, X.y), pk2(Y.x, Y.y), pk2(Z.x, Z.y)), d0, d1);
         unpk2(s4_d2_x2(qx2, qy2, qz2, pk2(X.z, X.w), pk2(Y.z, Y.w), pk2(Z.z, Z.w)), d2, d3);
-        m = min3f(m, d0, d1);
-        m = min3f(m, d2, d3);
+        if (g % 2 == 0) mg[g / 2] = fminf(d0, d1); else mg[g / 2] = min3f(mg[g / 2], d0, d1);
+        mg[g / 2] = min3f(mg[g / 2], d2, d3);
     }
+    float m = fminf(min3f(mg[0], mg[1], mg[2]), mg[3]);
+    static_assert(TT_LEAF == 32, "four runs of 8 vertices per tile");
     if (m <= best_d && m < inf) {
         // this tile holds a vertex at least as near as the best so far: the lowest index among the
-        // vertices at distance exactly m (scalar S4 rounds like the packed form)
-        const uint4* pi = reinterpret_cast<const uint4*>(tp + 3 * TT_LEAF);
-        uint32_t mi = 0xFFFFFFFFu;
-#pragma unroll 2
-        for (int g = 0; g < TT_LEAF / 4; ++g) {
-            const float4 X = __ldg(px + g), Y = __ldg(py + g), Z = __ldg(pz + g);
-            const uint4 I = __ldg(pi + g);
-            mi = (s4_d2(x, y, z, X.x, Y.x, Z.x) == m && I.x < mi) ? I.x : mi;
-            mi = (s4_d2(x, y, z, X.y, Y.y, Z.y) == m && I.y < mi) ? I.y : mi;
-            mi = (s4_d2(x, y, z, X.z, Y.z, Z.z) == m && I.z < mi) ? I.z : mi;
-            mi = (s4_d2(x, y, z, X.w, Y.w, Z.w) == m && I.w < mi) ? I.w : mi;
-        }
+        // vertices at distance exactly m, looked for only in the runs of 8 whose minimum is m
+        const int runs = (mg[0] == m ? 1 : 0) | (mg[1] == m ? 2 : 0) | (mg[2] == m ? 4 : 0) | (mg[3] == m ? 8 : 0);
+        const uint32_t mi = tt_lowest_index_at(tp, x, y, z, m, runs);
         const unsigned long long k = ((unsigned long long)__float_as_uint(m) << 32) | (unsigned long long)(index_offset + mi);
         if (k < best) { best = k; best_d = m; }
     }
+}
+
+// Seeds for the brute-force kernels' FIRST pass: every query descends the tile tree greedily (the child
+// box nearest to it at every level) and takes the nearest vertex of the tile it lands in.  Not the
+// nearest neighbour in general -- a real vertex of this shard close to the query, with its exact S4
+// distance, which is all the seeded brute-force kernels need to prune (any real vertex is a valid seed).
+__global__ void __launch_bounds__(128)
+k_tt_seed(const TileTree* __restrict__ tree_ptr, const float* __restrict__ qx, const float* __restrict__ qy,
+          const float* __restrict__ qz, long long n_queries, unsigned long long* __restrict__ keys,
+          uint32_t index_offset, const int* __restrict__ stop_flag)
+{
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_queries) return;
+    const TileTree& tree = *tree_ptr;
+    if (tree.n_levels <= 0) return;
+    const float inf = __int_as_float(0x7f800000);
+    const float x = qx[t], y = qy[t], z = qz[t];
+    int group = 0;
+    for (int lvl = tree.n_levels - 1; lvl >= 0; --lvl) {
+        const int c0 = group * TT_FAN, c1 = min(c0 + TT_FAN, tree.count[lvl]);
+        float bd = inf;
+        int bc = c0;
+        for (int c = c0; c < c1; ++c) {
+            const float4 lo = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c));
+            const float4 hi = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c) + 1);
+            if (lo.x > hi.x) continue;                       // empty box
+            float d = box_lower_bound(x, y, z, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+            d = (d >= 0.0f) ? fminf(d, 3.0e38f) : 3.0e38f;   // NaN query: any non-empty box
+            if (d < bd) { bd = d; bc = c; }
+        }
+        group = bc;
+    }
+    if (group >= tree.count[0]) return;
+    unsigned long long best = KEY_NONE;
+    float best_d = inf;
+    tt_scan_tile(tree.tiles + (size_t)group * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
+    if (best != KEY_NONE) keys[t] = best;
 }
 
 // FUSED (one GPU or query-sharded, no percentile): K1 in the prologue (q = imx2 @ (mx1 @ a), warm start
