@@ -75,7 +75,8 @@ typedef struct icp_params {
                                 returns the same keys.  Brute force: 1-6 direct metric, 20-24 expansion
                                 filter, 30-36 cylinder filter, 40-45 slab filter (default for seeded
                                 passes until round 2), 50-57 / 60-69 16-bit quantised slab test (alu-only /
-                                split fma+alu loop; default for seeded passes: 62).  BVH: 10 per-thread walk, 11 packet walk without the fused
+                                split fma+alu loops; default for seeded passes: 71).  Tree (ICP_NN_BVH): default = warp walk over a 32-ary tree of Morton tiles; 12 = binary LBVH
+                                packet walk, 10 per-thread walk, 11 packet walk without the fused
                                 epilogue.  Surface: 10 per-thread walk, 11 packet walk with eager
                                 triangle tests (default: deferred tests)                          */
     int32_t shard_mode;      /* icp_shard_mode when world_size > 1                               */

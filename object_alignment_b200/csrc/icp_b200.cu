@@ -1358,9 +1358,9 @@ int launch_nn(icp_handle* h, long long n_q)
         h->bf_warm_active = true;
     }
     if (q16_variant(variant) && !h->bf_warm_active) variant = 0;       // no seed (tiny shard / variant 59): cold pass below
-    if (variant == 59) variant = 62;
+    if (variant == 59) variant = 71;
     if (variant == 0) {
-        if (h->bf_warm_active && h->n_tiles >= 16) variant = 62;       // seeded: 16-bit slab kernel
+        if (h->bf_warm_active && h->n_tiles >= 16) variant = 71;       // seeded: 16-bit slab kernel
         else variant = h->n_tiles >= 256 ? 20 : 2;                     // cold: filter / direct kernel
     }
     if (q16_variant(variant)) {

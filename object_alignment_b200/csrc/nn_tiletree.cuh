@@ -120,7 +120,11 @@ constexpr float TT_GROW = 1.000002f;   // 2e-6 relative on the radius: > the fp3
 // lowest index among the vertices of a tile at S4 distance exactly m, looking only at the runs of 8 vertices
 // named by `runs` (out of line: keeps the scan's 24 vector loads from staying live; scalar S4 rounds
 // like the packed form)
-__device__ __noinline__ uint32_t tt_lowest_index_at(const float* __restrict__ tp, float x, float y, float z, float m, int runs)
+template <bool SMEM> __device__ __forceinline__ float4 tt_ld(const float4* p) { return SMEM ? *p : __ldg(p); }
+template <bool SMEM> __device__ __forceinline__ uint4 tt_ld(const uint4* p) { return SMEM ? *p : __ldg(p); }
+
+template <bool SMEM>
+__device__ __noinline__ uint32_t tt_lowest_index_at(const float* tp, float x, float y, float z, float m, int runs)
 {
     const float4* px = reinterpret_cast<const float4*>(tp);
     const float4* py = reinterpret_cast<const float4*>(tp + TT_LEAF);
@@ -131,8 +135,8 @@ __device__ __noinline__ uint32_t tt_lowest_index_at(const float* __restrict__ tp
         if (!((runs >> h) & 1)) continue;
 #pragma unroll
         for (int g = 2 * h; g < 2 * h + 2; ++g) {
-            const float4 X = __ldg(px + g), Y = __ldg(py + g), Z = __ldg(pz + g);
-            const uint4 I = __ldg(pi + g);
+            const float4 X = tt_ld<SMEM>(px + g), Y = tt_ld<SMEM>(py + g), Z = tt_ld<SMEM>(pz + g);
+            const uint4 I = tt_ld<SMEM>(pi + g);
             mi = (s4_d2(x, y, z, X.x, Y.x, Z.x) == m && I.x < mi) ? I.x : mi;
             mi = (s4_d2(x, y, z, X.y, Y.y, Z.y) == m && I.y < mi) ? I.y : mi;
             mi = (s4_d2(x, y, z, X.z, Y.z, Z.z) == m && I.z < mi) ? I.z : mi;
@@ -143,7 +147,8 @@ __device__ __noinline__ uint32_t tt_lowest_index_at(const float* __restrict__ tp
 }
 
 // Scan one leaf tile for this lane's query: running minimum with packed math, exact key on demand.
-__device__ __forceinline__ void tt_scan_tile(const float* __restrict__ tp, float x, float y, float z,
+template <bool SMEM>
+__device__ __forceinline__ void tt_scan_tile(const float* tp, float x, float y, float z,
                                              uint32_t index_offset, unsigned long long& best, float& best_d)
 {
     const float inf = __int_as_float(0x7f800000);
@@ -154,7 +159,7 @@ __device__ __forceinline__ void tt_scan_tile(const float* __restrict__ tp, float
     float mg[TT_LEAF / 8];                                   // minimum per run of 8 vertices
 #pragma unroll
     for (int g = 0; g < TT_LEAF / 4; ++g) {                  // warp-uniform addresses: one transaction each
-        const float4 X = __ldg(px + g), Y = __ldg(py + g), Z = __ldg(pz + g);
+        const float4 X = tt_ld<SMEM>(px + g), Y = tt_ld<SMEM>(py + g), Z = tt_ld<SMEM>(pz + g);
         float d0, d1, d2, d3;
         unpk2(s4_d2_x2(qx2, qy2, qz2, pk2(X.x, X.y), pk2(Y.x, Y.y), pk2(Z.x, Z.y)), d0, d1);
         unpk2(s4_d2_x2(qx2, qy2, qz2, pk2(X.z, X.w), pk2(Y.z, Y.w), pk2(Z.z, Z.w)), d2, d3);
@@ -167,7 +172,7 @@ __device__ __forceinline__ void tt_scan_tile(const float* __restrict__ tp, float
         // this tile holds a vertex at least as near as the best so far: the lowest index among the
         // vertices at distance exactly m, looked for only in the runs of 8 whose minimum is m
         const int runs = (mg[0] == m ? 1 : 0) | (mg[1] == m ? 2 : 0) | (mg[2] == m ? 4 : 0) | (mg[3] == m ? 8 : 0);
-        const uint32_t mi = tt_lowest_index_at(tp, x, y, z, m, runs);
+        const uint32_t mi = tt_lowest_index_at<SMEM>(tp, x, y, z, m, runs);
         const unsigned long long k = ((unsigned long long)__float_as_uint(m) << 32) | (unsigned long long)(index_offset + mi);
         if (k < best) { best = k; best_d = m; }
     }
@@ -207,15 +212,26 @@ k_tt_seed(const TileTree* __restrict__ tree_ptr, const float* __restrict__ qx, c
     if (group >= tree.count[0]) return;
     unsigned long long best = KEY_NONE;
     float best_d = inf;
-    tt_scan_tile(tree.tiles + (size_t)group * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
+    tt_scan_tile<false>(tree.tiles + (size_t)group * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
     if (best != KEY_NONE) keys[t] = best;
+}
+
+// one 512-byte leaf tile global -> shared, 16 bytes per lane (LDGSTS), and the group bookkeeping
+__device__ __forceinline__ void tt_prefetch_tile(float* dst, const float* __restrict__ src, int lane)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
+                 ::"r"(smem_u32(dst + 4 * lane)), "l"(src + 4 * lane) : "memory");
+}
+template <int N> __device__ __forceinline__ void tt_wait_prefetch()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // FUSED (one GPU or query-sharded, no percentile): K1 in the prologue (q = imx2 @ (mx1 @ a), warm start
 // from the previous winner) and K3 + K4 (world distance, thresh, target, fp64 moment partials) in the
 // epilogue, like k_nn_bvh_packet<true>.
 template <bool FUSED>
-__global__ void __launch_bounds__(TT_THREADS)
+__global__ void __launch_bounds__(TT_THREADS, 1024 / TT_THREADS)       // <= 64 registers: 8 CTAs of 128 threads per SM
 k_nn_tiletree(const TileTree* __restrict__ tree_ptr, const float* __restrict__ qx, const float* __restrict__ qy,
               const float* __restrict__ qz, const DevState* __restrict__ st,
               const float4* __restrict__ mov_slots, const float4* __restrict__ base4, long long base_off,
@@ -224,6 +240,7 @@ k_nn_tiletree(const TileTree* __restrict__ tree_ptr, const float* __restrict__ q
 {
     if (st->converged) return;
     __shared__ int s_stack[TT_THREADS / 32][TT_STACK];
+    __shared__ __align__(16) float s_tile[TT_THREADS / 32][2][TT_TILE_FLOATS];   // per warp: two leaf tiles in flight
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = t < n_queries;
@@ -278,7 +295,7 @@ k_nn_tiletree(const TileTree* __restrict__ tree_ptr, const float* __restrict__ q
                 group = group * TT_FAN + (__ffs(who) - 1);
             }
             if (group < tree.count[0])
-                tt_scan_tile(tree.tiles + (size_t)group * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
+                tt_scan_tile<false>(tree.tiles + (size_t)group * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
         }
 
         // ---- walk: groups of 32 boxes against the warp's patch box, one box per lane -------------------
@@ -325,21 +342,51 @@ k_nn_tiletree(const TileTree* __restrict__ tree_ptr, const float* __restrict__ q
             }
             unsigned keep = 0u;
             bool improved = false;
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float lx = __shfl_sync(0xffffffffu, clo.x, b), ly = __shfl_sync(0xffffffffu, clo.y, b),
-                            lz = __shfl_sync(0xffffffffu, clo.z, b), hx = __shfl_sync(0xffffffffu, chi.x, b),
-                            hy = __shfl_sync(0xffffffffu, chi.y, b), hz = __shfl_sync(0xffffffffu, chi.z, b);
-                const float d = box_lower_bound(x, y, z, lx, ly, lz, hx, hy, hz);
-                // same prune rule as nn_bvh.cuh: skip only when the shrunk bound is STRICTLY greater
-                if (!__any_sync(0xffffffffu, active && !(d * BVH_SHRINK > best_d))) continue;
-                if (lvl > 0) {
-                    keep |= 1u << b;
-                } else {                                 // a leaf tile some lane needs: scan it now, with the bounds as they are
-                    const float before = best_d;
-                    tt_scan_tile(tree.tiles + (size_t)(group * TT_FAN + b) * TT_TILE_FLOATS, x, y, z, index_offset, best, best_d);
-                    improved = improved || (best_d < before);
+            // next candidate box (lowest set bit first) that some lane's own ball still reaches, or -1;
+            // same prune rule as nn_bvh.cuh: skip only when the shrunk bound is STRICTLY greater
+            auto next_needed = [&](unsigned& m_) -> int {
+                while (m_) {
+                    const int b = __ffs(m_) - 1;
+                    m_ &= m_ - 1;
+                    const float lx = __shfl_sync(0xffffffffu, clo.x, b), ly = __shfl_sync(0xffffffffu, clo.y, b),
+                                lz = __shfl_sync(0xffffffffu, clo.z, b), hx = __shfl_sync(0xffffffffu, chi.x, b),
+                                hy = __shfl_sync(0xffffffffu, chi.y, b), hz = __shfl_sync(0xffffffffu, chi.z, b);
+                    const float d = box_lower_bound(x, y, z, lx, ly, lz, hx, hy, hz);
+                    if (__any_sync(0xffffffffu, active && !(d * BVH_SHRINK > best_d))) return b;
+                }
+                return -1;
+            };
+            if (lvl > 0) {
+                for (int b = next_needed(mask); b >= 0; b = next_needed(mask)) keep |= 1u << b;
+            } else {
+                // leaf tiles: the next needed tile is copied into shared memory (one 16-byte LDGSTS per lane)
+                // while the current one is scanned, so the walk does not sit out a global-memory latency
+                // per tile; a prefetched tile that the improved bounds no longer need is simply dropped
+                int buf = 0;
+                int b = next_needed(mask);
+                if (b >= 0) tt_prefetch_tile(s_tile[warp][0], tree.tiles + (size_t)(group * TT_FAN + b) * TT_TILE_FLOATS, lane);
+                while (b >= 0) {
+                    const int nb = next_needed(mask);
+                    if (nb >= 0) {
+                        tt_prefetch_tile(s_tile[warp][buf ^ 1], tree.tiles + (size_t)(group * TT_FAN + nb) * TT_TILE_FLOATS, lane);
+                        tt_wait_prefetch<1>();
+                    } else {
+                        tt_wait_prefetch<0>();
+                    }
+                    __syncwarp();
+                    // the bounds may have improved since `b` was chosen: one more look before the scan
+                    const float lx = __shfl_sync(0xffffffffu, clo.x, b), ly = __shfl_sync(0xffffffffu, clo.y, b),
+                                lz = __shfl_sync(0xffffffffu, clo.z, b), hx = __shfl_sync(0xffffffffu, chi.x, b),
+                                hy = __shfl_sync(0xffffffffu, chi.y, b), hz = __shfl_sync(0xffffffffu, chi.z, b);
+                    const float d = box_lower_bound(x, y, z, lx, ly, lz, hx, hy, hz);
+                    if (__any_sync(0xffffffffu, active && !(d * BVH_SHRINK > best_d))) {
+                        const float before = best_d;
+                        tt_scan_tile<true>(s_tile[warp][buf], x, y, z, index_offset, best, best_d);
+                        improved = improved || (best_d < before);
+                    }
+                    __syncwarp();                        // everyone is done with s_tile[buf] before it is refilled
+                    b = nb;
+                    buf ^= 1;
                 }
             }
             if (lvl > 0) {
