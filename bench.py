@@ -181,10 +181,9 @@ class CpuReference:
     def step(self, stride):
         """One sampled iteration body (icp_align.py:101-109); returns (seconds, queries, pairs kept)."""
         import contextlib
-        import io
 
         t0 = time.perf_counter()
-        with contextlib.redirect_stdout(io.StringIO()):          # general.py:309 prints per vertex
+        with open(os.devnull, "w") as sink, contextlib.redirect_stdout(sink):      # general.py:309 prints per vertex
             A, B, ds = self.make_pairs(self.align, self.base, self.bvh, self.vlist, self.thresh, stride, True)
             self.solve(A, B, shear=False, scale=False, usesvd=True)
         return time.perf_counter() - t0, len(self.vlist[0::stride] if stride > 1 else self.vlist), A.shape[1]
@@ -381,8 +380,9 @@ def sharded_parity(eng, cfg, vlist, local_rank, rank, pairs_sharded, steps, args
 # instructions per (query, base vertex) pair in the hot loop of each brute-force kernel, counted in the SASS
 # (profiles/r2_sass_*.txt): (issue slots, alu-pipe cycles, fma-pipe cycles) per pair and lane
 K2_MODELS = {
-    "k_nn_bruteforce_q16<split>": dict(issue=0.75 + 1.0 / 32, alu=0.5, fma=0.5,
-                                       mix="per 8 vertices: 1/R LDS.128 + 4 IMAD.IADD (fma pipe) + 2 VIMNMX3.U16x2 (alu pipe, 2 cycles each)"),
+    "k_nn_bruteforce_q16<split>": dict(issue=0.625 + 1.0 / 32, alu=0.75, fma=0.5,
+                                       mix="per 8 vertices and query: 2 VIADDMNMX.U16x2 + 1 VIMNMX3.U16x2 (alu pipe, 2 cycles each) "
+                                           "+ 2 IMAD (fmaheavy pipe, 2 cycles each); 1 LDS.128 per 4 queries"),
     "k_nn_bruteforce_q16<alu>": dict(issue=0.5 + 1.0 / 32, alu=1.0, fma=0.0,
                                      mix="per 8 vertices: 1/R LDS.128 + 4 VIADDMNMX.U16x2 (alu pipe, 2 cycles each)"),
     "k_nn_bruteforce_slab": dict(issue=1.0 + 1.0 / 16, alu=1.0, fma=1.0, mix="per 4 vertices: 2 FFMA2 + 2 FMNMX3 + 2/R LDS.128"),
@@ -397,7 +397,7 @@ def bruteforce_kernel_name(variant, n_local):
     tiles = (n_local + 1023) // 1024
     if variant == 0:
         return "k_nn_bruteforce_q16<split>" if tiles >= 16 else "k_nn_bruteforce"
-    if 60 <= variant <= 69 or variant == 58:
+    if 60 <= variant <= 79 or variant in (58, 59):
         return "k_nn_bruteforce_q16<split>"
     if 50 <= variant <= 57:
         return "k_nn_bruteforce_q16<alu>"
