@@ -620,7 +620,8 @@ def run_ours(args, rank, world, local_rank):
     final_pose = r["pose"]
 
     # ---- end-to-end through the public API with host buffers -------------------------------
-    upload = eng.set_moving_collective if (world > 1 and not shard_q and hasattr(eng, "set_moving_collective")) else eng.set_moving
+    collective_upload = world > 1 and not shard_q
+    upload = eng.set_moving_collective if collective_upload else eng.set_moving
     eng.set_matrices(ident, ident)
     eng.reset_convergence()
     pose = ident.copy()
@@ -638,7 +639,6 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     if dist is not None:
         e2e_s = icpdist.allreduce_max_scalar(e2e_s, dist)
-    collective_upload = upload is not eng.set_moving
     h2d = (mov.nbytes // world if collective_upload else mov.nbytes) + 2 * 64 + (vlist.nbytes if vlist is not None else 0)
     d2h = 16 * 8 + 168 + 64
 

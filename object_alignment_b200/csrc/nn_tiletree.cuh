@@ -203,7 +203,11 @@ k_tt_seed(const TileTree* __restrict__ tree_ptr, const float* __restrict__ qx, c
             const float4 lo = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c));
             const float4 hi = __ldg(tree.boxes + 2 * (size_t)(tree.offset[lvl] + c) + 1);
             if (lo.x > hi.x) continue;                       // empty box
+            // nearest box first; among the (fat, overlapping) boxes that contain the query the lower bound is 0
+            // for all of them, so the distance to the box centre breaks the tie
             float d = box_lower_bound(x, y, z, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+            const float cx = 0.5f * (lo.x + hi.x) - x, cy = 0.5f * (lo.y + hi.y) - y, cz = 0.5f * (lo.z + hi.z) - z;
+            d += 0.25f * (cx * cx + cy * cy + cz * cz);
             d = (d >= 0.0f) ? fminf(d, 3.0e38f) : 3.0e38f;   // NaN query: any non-empty box
             if (d < bd) { bd = d; bc = c; }
         }
