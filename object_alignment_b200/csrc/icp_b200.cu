@@ -505,9 +505,9 @@ __global__ void k_solve_update(DevState* st, const double* __restrict__ moments,
     solve_update_body(st, moments, scale_mode, use_target, target_d, stats, stats_capacity);
 }
 
-__device__ void solve_update_body(DevState* st, const double* __restrict__ moments, int scale_mode,
-                                  int use_target, double target_d, icp_iter_stats* __restrict__ stats,
-                                  int stats_capacity)
+__device__ __noinline__ void solve_update_body(DevState* st, const double* __restrict__ moments, int scale_mode,
+                                               int use_target, double target_d, icp_iter_stats* __restrict__ stats,
+                                               int stats_capacity)
 {
     double M[16], mean_d, std_d;
     if (!solve_from_moments(moments, st->shift, scale_mode, M, &mean_d, &std_d)) {
@@ -822,6 +822,16 @@ struct icp_handle {
     TileTree* d_tt_desc = nullptr;
     TileTree tt{};
     bool tt_built = false;
+    // second-generation walk (k_nn_tiletree_p): batch queue, winner tiles per slot, ticket tree of moment partials
+    TTQueue* d_tt_queue = nullptr;
+    int* d_win_tile = nullptr;
+    long long win_tile_capacity = 0;
+    bool tt_win_valid = false;             // d_win_tile matches d_keys (the last pass was a tile-tree walk over these slots)
+    double* d_tt_part = nullptr;
+    unsigned int* d_tt_tickets = nullptr;
+    long long tt_tail_batches = 0;         // what d_tt_part / d_tt_tickets were sized for
+    TTTail tt_tail{};
+    int tt_grid = 0;                       // persistent grid of the walk (CTAs)
     // query slots in Morton order of the moving vertices (BVH mode) + warm start bookkeeping
     uint32_t* d_slot_pos = nullptr;
     uint32_t* d_pos_slot = nullptr;
@@ -1526,17 +1536,90 @@ int build_tiletree(icp_handle* h)
 // vertex tree searches: 0 (default) = warp walk over the 32-ary tile tree; 12 = binary LBVH packet walk;
 // 10 = LBVH per-thread walk; 98, 99 = LBVH walks with visit counters
 bool tiletree_variant(const icp_handle* h) { return h->prm.nn_variant == 0 || h->prm.nn_variant == 13; }
+bool tiletree_persistent(const icp_handle* h) { return h->prm.nn_variant == 0; }   // 13 = first generation (one CTA per 128 slots)
+
+// queue, winner tiles and (fused) the ticket tree for n_q query slots; the persistent grid
+int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused)
+{
+    if (!h->d_tt_queue) {
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_queue, sizeof(TTQueue)));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_tt_queue, 0, sizeof(TTQueue), h->stream));
+    }
+    if (n_q > h->win_tile_capacity || !h->d_win_tile) {
+        if (h->d_win_tile) cudaFree(h->d_win_tile);
+        h->d_win_tile = nullptr; h->win_tile_capacity = 0; h->tt_win_valid = false;
+        const long long cap = std::max<long long>(n_q, 1);
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_win_tile, (size_t)cap * sizeof(int)));
+        h->win_tile_capacity = cap;
+    }
+    const long long nb = (n_q + 31) / 32;
+    if (fused && (nb != h->tt_tail_batches || !h->d_tt_part)) {
+        TTTail& t = h->tt_tail;
+        memset(&t, 0, sizeof(t));
+        long long part = 0, tickets = 0, c = nb;
+        int lv = 0;
+        for (; lv < TT_TAIL_LEVELS; ++lv) {
+            const long long groups = (c + 31) / 32;
+            t.count[lv] = (int)c; t.part_off[lv] = part; t.ticket_off[lv] = (int)tickets;
+            part += groups * 32 * MOM; tickets += groups;
+            if (c <= 32) { ++lv; break; }
+            c = groups;
+        }
+        if (nb > 0 && t.count[lv - 1] > 32) return fail(h, ICP_ERR_BAD_ARG, "tile tree: too many query slots");
+        if (h->d_tt_part) cudaFree(h->d_tt_part);
+        if (h->d_tt_tickets) cudaFree(h->d_tt_tickets);
+        h->d_tt_part = nullptr; h->d_tt_tickets = nullptr;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_part, (size_t)std::max<long long>(part, 1) * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_tickets, (size_t)std::max<long long>(tickets, 1) * sizeof(unsigned int)));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_tt_tickets, 0, (size_t)std::max<long long>(tickets, 1) * sizeof(unsigned int), h->stream));
+        h->tt_tail_batches = nb;
+    }
+    if (h->tt_grid == 0) {
+        int occ_f = 1, occ_p = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_nn_tiletree_p<true>, TT_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k_nn_tiletree_p<false>, TT_THREADS, 0);
+        h->tt_grid = h->sm_count * std::max(1, std::min(occ_f, occ_p));
+    }
+    return ICP_OK;
+}
+
+template <bool FUSED>
+int launch_tiletree_walk(icp_handle* h, long long n_q, int solve)
+{
+    const long long nb = (n_q + 31) / 32;
+    const int g = (int)std::max<long long>(1, std::min<long long>((nb + TT_THREADS / 32 - 1) / (TT_THREADS / 32), h->tt_grid));
+    TTTail tail = h->tt_tail;
+    tail.part = h->d_tt_part; tail.tickets = h->d_tt_tickets; tail.moments = h->d_moments;
+    tail.stats = h->d_stats; tail.stats_capacity = h->stats_capacity;
+    tail.solve = solve; tail.scale_mode = h->prm.align_meth == 1; tail.use_target = h->prm.use_target; tail.target_d = h->prm.target_d;
+    float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+    const int warm = (h->warm_valid ? 1 : 0) | ((h->warm_valid && h->tt_win_valid) ? 2 : 0);
+    k_nn_tiletree_p<FUSED><<<g, TT_THREADS, 0, h->stream>>>(
+        h->tt, FUSED ? nullptr : qx, FUSED ? nullptr : qy, FUSED ? nullptr : qz, h->d_state,
+        FUSED ? h->d_mov_slots : nullptr, FUSED ? h->d_base4 : nullptr, h->base_off, h->n_local, h->prm.thresh, warm, n_q,
+        h->d_keys, h->d_win_tile, (uint32_t)h->base_off, h->d_tt_queue, tail);
+    h->launches++;
+    h->tt_win_valid = true;
+    CUDA_TRY(h, cudaGetLastError());
+    return ICP_OK;
+}
 
 int launch_nn_bvh(icp_handle* h, long long n_q)
 {
     if (n_q <= 0 || h->n_local <= 0) return ICP_OK;
     int rc = tiletree_variant(h) ? build_tiletree(h) : build_bvh(h);
     if (rc) return rc;
+    if (tiletree_persistent(h)) {
+        rc = ensure_tiletree_walk(h, n_q, false);
+        if (rc) return rc;
+    }
     ProfScope ps(h, 0);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     const unsigned g128 = (unsigned)((n_q + 127) / 128);
     const unsigned gpk = (unsigned)((n_q + PKT_THREADS - 1) / PKT_THREADS);
     const int v = h->prm.nn_variant;
+    if (tiletree_persistent(h)) return launch_tiletree_walk<false>(h, n_q, 0);
+    h->tt_win_valid = false;
     if (tiletree_variant(h)) {
         k_nn_tiletree<false><<<(unsigned)((n_q + TT_THREADS - 1) / TT_THREADS), TT_THREADS, 0, h->stream>>>(
             h->d_tt_desc, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0, n_q, h->d_keys,
@@ -1823,12 +1906,42 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     const int g = (int)std::max<long long>(1, (n_q + cta - 1) / cta);
     rc = ensure_partials(h, g);
     if (rc) return rc;
+    const bool persistent = tiletree && tiletree_persistent(h) && n_q > 0;
+    if (persistent) {
+        rc = ensure_tiletree_walk(h, n_q, true);
+        if (rc) return rc;
+    }
     if (h->pose_dirty) {
         ProfScope ps(h, 3);
         k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
         h->launches += 1;
         h->pose_dirty = false;
     }
+    if (persistent) {
+        // the whole iteration is ONE launch on one GPU: walk + filter + moments + ticketed reduction + solve
+        {
+            ProfScope ps(h, 0);
+            rc = launch_tiletree_walk<true>(h, n_q, h->prm.world_size == 1 ? 1 : 0);
+            if (rc) return rc;
+        }
+        h->warm_valid = true;
+        h->bf_warm_valid = false;
+        if (h->prm.world_size > 1) {      // queries sharded: the only exchange is the 20-double moment sum
+            if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
+            {
+                ProfScope ps(h, 4);
+                NCCL_TRY(h, g_nccl.AllReduce(h->d_moments, h->d_moments, MOM, ncclDouble, ncclSum, h->comm, h->stream));
+            }
+            ProfScope ps(h, 2);
+            k_solve_update<<<1, 32, 0, h->stream>>>(h->d_state, h->d_moments, h->prm.align_meth == 1,
+                                                    h->prm.use_target, h->prm.target_d, h->d_stats,
+                                                    h->stats_capacity);
+            h->launches += 1;
+        }
+        CUDA_TRY(h, cudaGetLastError());
+        return ICP_OK;
+    }
+    h->tt_win_valid = false;
     {
         ProfScope ps(h, 0);
         if (h->surface && (h->prm.nn_variant == 11 || h->n_local >= (1ll << 27)))
@@ -2080,7 +2193,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound, h->d_tt_boxes, h->d_tt_tiles, h->d_tt_desc};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound, h->d_tt_boxes, h->d_tt_tiles, h->d_tt_desc, h->d_tt_queue, h->d_win_tile, h->d_tt_part, h->d_tt_tickets};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }

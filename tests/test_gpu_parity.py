@@ -213,7 +213,7 @@ def _clouds_for_bvh(case):
     raise KeyError(case)
 
 
-TREE_VARIANTS = [0, 12, 10]      # tile-tree warp walk (default), LBVH packet walk, LBVH per-thread walk
+TREE_VARIANTS = [0, 13, 12, 10]      # tile-tree walk (default: persistent warps; 13: first generation), LBVH packet walk, LBVH per-thread walk
 
 
 @pytest.mark.parametrize("variant", TREE_VARIANTS)
@@ -234,7 +234,7 @@ def test_bvh_matches_bruteforce_oracle(case, variant):
 
 @pytest.mark.parametrize("n_base,n_mov", [(1, 1), (1, 300), (7, 9), (8, 8), (9, 100), (1023, 1),
                                           (1025, 1025), (4097, 2049), (33, 70), (1056, 31), (40000, 5)])
-@pytest.mark.parametrize("variant", [0, 12])
+@pytest.mark.parametrize("variant", [0, 13, 12])
 def test_bvh_ragged_sizes(n_base, n_mov, variant):
     base = _rand_cloud(n_base, 10 + n_base)
     mov = _rand_cloud(n_mov, 20 + n_mov)
@@ -408,7 +408,7 @@ def test_stepwise_parity_against_oracle(name):
             np.testing.assert_array_equal(e.matrix_world(), ms.matmul44(mw, M.astype(np.float32)))
 
 
-@pytest.mark.parametrize("variant", [0, 12])
+@pytest.mark.parametrize("variant", [0, 13, 12])
 def test_bvh_warm_start_stays_exact_over_iterations(variant):
     """BVH mode re-uses last iteration's winner as the initial bound; every iteration's keys must
     still equal the brute-force oracle evaluated at the engine's own current pose."""
