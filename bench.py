@@ -378,7 +378,7 @@ def sharded_parity(eng, cfg, vlist, local_rank, rank, pairs_sharded, steps, args
 
 
 # instructions per (query, base vertex) pair in the hot loop of each brute-force kernel, counted in the SASS
-# (profiles/r2_sass_*.txt): (issue slots, alu-pipe cycles, fma-pipe cycles) per pair and lane
+# (profiles/r2_ncu_k2_q16_summary.txt): (issue slots, alu-pipe cycles, fma-pipe cycles) per pair and lane
 K2_MODELS = {
     "k_nn_bruteforce_q16<split>": dict(issue=0.625 + 1.0 / 32, alu=0.75, fma=0.5,
                                        mix="per 8 vertices and query: 2 VIADDMNMX.U16x2 + 1 VIMNMX3.U16x2 (alu pipe, 2 cycles each) "
@@ -446,7 +446,7 @@ def bruteforce_roofline(kernel, m, n_local, nn_avg_ms, share, sm_mhz, sm_count, 
                        "instruction per cycle" % (smsp, sm_mhz),
         "model": {"instructions_per_pair": mdl["issue"], "alu_cycles_per_pair": mdl["alu"],
                   "fma_cycles_per_pair": mdl["fma"], "hot_loop": mdl["mix"],
-                  "source": "SASS of the hot loop, profiles/r2_sass_k2_q16.txt; slow paths and tile set-up "
+                  "source": "SASS of the hot loop, profiles/r2_ncu_k2_q16_summary.txt (hot loop as executed, with per-instruction samples); slow paths and tile set-up "
                             "(measured 7 % of the executed instructions) are NOT counted as useful work"},
         "pipe_utilisation": {"issue": util["issue"], "alu": util["alu"], "fma": util["fma"]},
         "ncu_measured": measured,
@@ -465,21 +465,28 @@ def bruteforce_roofline(kernel, m, n_local, nn_avg_ms, share, sm_mhz, sm_count, 
     }
 
 
-def bvh_roofline(m, n_local, avg_ms, hbm_peak, workload, kernel="k_nn_bvh_packet<fused>"):
-    """Roofline of the tree search: compulsory DRAM bytes per launch = queries in (12 B) + keys read and
-    written (16 B) per query + one pass over the tree (64 B per 16-vertex run) and the sorted
-    vertices (16 B each).  The walk itself is served by L1/L2 (the index of a 1M-vertex base is 24 MB
-    against a 126 MB L2), so this fraction is small by construction."""
-    compulsory = 28.0 * m + (16.0 + 4.0) * n_local
+TREE_KERNELS = {0: "k_nn_tiletree_p<fused>", 13: "k_nn_tiletree<fused>", 12: "k_nn_bvh_packet<fused>"}
+
+
+def bvh_roofline(m, n_local, avg_ms, hbm_peak, workload, kernel="k_nn_tiletree_p<fused>"):
+    """Roofline of the tree search: compulsory DRAM bytes per launch with a cold L2.  Tile tree: per query the
+    moving slot (16 B), the key read and written (16 B) and the winner's tile read and written (8 B); per
+    base vertex its leaf tile (16 B), its share of the boxes (1 B) and the float4 copy the seed / winner
+    gathers touch (16 B).  The walk itself is served by L1/L2 (the index of a 1M-vertex base is 17 MB
+    against a 126 MB L2), so this fraction is small by construction: the kernel is bound by instruction
+    issue and dependent-load latency, which `ncu_measured` shows."""
+    compulsory = 40.0 * m + 33.0 * n_local
     traffic = load_profile_json("nn_traffic.json").get(workload + "_bvh")
     ach = compulsory / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
     return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
             "frac": ach / hbm_peak if ach else None, "traffic": traffic,
-            "algorithmic": "28 B per query + 20 B per base vertex (index read once)",
+            "algorithmic": "40 B per query + 33 B per base vertex (index and float4 copy read once)",
             "avg_launch_ms": avg_ms, "queries_per_s": m / (avg_ms * 1e-3) if avg_ms > 0 else None,
             "dram_gbs_from_traffic": (traffic / (avg_ms * 1e-3) / 1e9) if (traffic and avg_ms > 0) else None,
             "ncu_measured": load_profile_json("nn_pipes.json").get(kernel),
-            "note": "latency/issue-bound tree walk served from L1/L2; see ncu_measured for the executed-work view"}
+            "note": "issue- and latency-bound tree walk served from L1/L2; in tree mode the launch is the whole "
+                    "iteration (walk + filter + moments + ticketed reduction + solve); see ncu_measured for the "
+                    "executed-work view"}
 
 
 def execute_total(cfg, local_rank, mode, iters=50):
@@ -670,7 +677,7 @@ def run_ours(args, rank, world, local_rank):
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     if nn_mode != 0:
         roofline = bvh_roofline(m_eff // (world if shard_q else 1), n_local, nn_avg_ms, hbm_peak_of(peaks), args.workload,
-                                "k_nn_surface_defer<fused>" if surface else "k_nn_bvh_packet<fused>")
+                                "k_nn_surface_defer<fused>" if surface else TREE_KERNELS.get(args.nn_variant, "k_nn_bvh_packet<fused>"))
     else:
         roofline = bruteforce_roofline(bruteforce_kernel_name(args.nn_variant, n_local), m_eff, n_local, nn_avg_ms,
                                        nn_ms / sum(step_ms), sm_mhz, 148, fp32_peak, peaks, args.workload)

@@ -747,10 +747,10 @@ k_nn_tiletree_p(const __grid_constant__ TileTree tree, const float* __restrict__
                 // The patch box is only a summary: every candidate box is re-tested against each lane's OWN
                 // ball, lane = query, before anything is pushed or scanned; same prune rule as nn_bvh.cuh
                 // (skip only when the shrunk bound is STRICTLY greater)
-                auto needs = [&](int b) -> bool {
+                auto needs = [&](int b) -> unsigned {          // the lanes whose own ball reaches candidate box b
                     const float4 l = s_box[warp][2 * b], h = s_box[warp][2 * b + 1];
                     const float d = box_lower_bound(x, y, z, l.x, l.y, l.z, h.x, h.y, h.z);
-                    return __any_sync(0xffffffffu, active && !(d * BVH_SHRINK > best_d));
+                    return __ballot_sync(0xffffffffu, active && !(d * BVH_SHRINK > best_d));
                 };
                 auto next_needed = [&](unsigned& m_) -> int {
                     while (m_) {
@@ -787,7 +787,11 @@ k_nn_tiletree_p(const __grid_constant__ TileTree tree, const float* __restrict__
                             tt_wait_prefetch<0>();
                         }
                         __syncwarp();
-                        if (needs(b))                        // the bounds may have improved since `b` was chosen
+                        const unsigned who = needs(b);       // the bounds may have improved since `b` was chosen
+#ifdef ICP_TT_STATS
+                        if (lane == 0 && who) { const int k = __popc(who); atomicAdd(&g_bvh_counters[k <= 2 ? 0 : (k <= 4 ? 1 : (k <= 8 ? 2 : 3))], 1ull); }
+#endif
+                        if (who)
                             improved = tt_fold_tile<true>(tree.tiles, s_tile[warp][buf], group * TT_FAN + b, active, x, y, z,
                                                           best_d, best_ref, best_idx) || improved;
                         __syncwarp();                        // everyone is done with s_tile[buf] before it is refilled
