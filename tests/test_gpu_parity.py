@@ -428,6 +428,30 @@ def test_bvh_warm_start_stays_exact_over_iterations(variant):
             np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(res["A"], res["B"]), atol=1e-10)
 
 
+@pytest.mark.parametrize("variant", [0, 13, 12])
+def test_tree_warm_start_on_a_lattice_resolves_ties_to_the_lowest_index(variant):
+    """Shift the pose by exactly one lattice cell: the previous winner (the seed) is now a higher-index TIE
+    of the new winner, usually in ANOTHER leaf tile.  The tile-tree walk defers the index look-up and must
+    resolve such ties between tiles on the spot; the fused step() passes in between keep the seeds warm."""
+    g = np.arange(28, dtype=np.float32)
+    base = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)     # 21952 vertices
+    mov = (base[::3] + np.float32(0.5)).astype(np.float32)
+    mov = mov[(mov < 26).all(axis=1)]
+    with IcpEngine(nn_mode=1, nn_variant=variant, thresh=1e9, use_target=False) as e:
+        e.set_base(base)
+        e.set_moving(mov)
+        for k, shift in enumerate(((0, 0, 0), (-1, 0, 0), (0, 1, 0), (0, 0, -1), (1, -1, 1), (0, 0, 0))):
+            mw = np.eye(4, dtype=np.float32)
+            mw[:3, 3] = shift
+            e.set_matrices(mw, np.eye(4))
+            if k % 2 == 1:
+                e.step()                              # fused kernel (seeds + winner tiles refreshed), pose moves
+                e.set_matrices(mw, np.eye(4))
+            idx, d2 = e.nn()
+            oi, od = orc.nn_bruteforce((mov + np.array(shift, np.float32)).astype(np.float32), base)
+            assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+
+
 @pytest.mark.parametrize("mode", ["bvh", "surface"])
 def test_tree_modes_keep_slot_order_and_seeds_across_same_shape_uploads(mode):
     """icp_set_moving with the same vertex count keeps the Morton slot order and the previous winners
@@ -469,7 +493,8 @@ def test_tree_modes_keep_slot_order_and_seeds_across_same_shape_uploads(mode):
         assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
 
 
-@pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36, 40, 41, 42, 44, 45, 50, 51, 52, 53, 54, 55, 56, 57])
+@pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36, 40, 41, 42, 44, 45, 50, 51, 52, 53, 54, 55, 56, 57,
+                                     58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73])
 def test_bruteforce_seeded_passes_stay_exact(variant):
     """From the second pass on the brute-force filter kernel starts its running minimum from the
     previous winner re-evaluated under the new pose.  Every pass must still return the oracle's
