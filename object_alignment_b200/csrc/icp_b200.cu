@@ -810,6 +810,13 @@ struct icp_handle {
     float* d_bound = nullptr;
     long long bound_capacity = 0;
     bool bound_active = false;             // the pass being enqueued has a valid d_bound
+    // q16 query classes: slots in class order (similar pruning radius together), rebuilt every pass
+    unsigned char* d_q16_cls = nullptr;    // cls | cls_out
+    uint32_t* d_q16_ids = nullptr;         // ids | perm
+    unsigned int* d_q16_hist = nullptr;    // 256 bins + the median bin
+    void* d_q16_sort_temp = nullptr;
+    size_t q16_sort_temp_bytes = 0;
+    long long q16_class_capacity = 0;
     std::vector<const void*> smem_configured;   // kernels whose dynamic-smem limit was raised on THIS device
     // spatial index (nn_mode == ICP_NN_BVH), built lazily from d_base4
     BvhNode* d_bvh_nodes = nullptr;
@@ -1084,7 +1091,7 @@ int launch_nn_filter_t(icp_handle* h, long long n_q)
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_filter_tiles, h->d_base_tiles, h->d_filter_info, h->n_tiles,
                                                 tiles_per_cta, qx, qy, qz, n_q, h->d_keys, (uint32_t)h->base_off,
-                                                h->bf_warm_active ? 1 : 0, &h->d_state->converged);
+                                                h->bf_warm_active ? 1 : 0, &h->d_state->converged, nullptr, nullptr);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return ICP_OK;
@@ -1318,9 +1325,11 @@ int build_q16(icp_handle* h, int want_order)
 template <int R, int STAGES, int CH, int MIX, int MINB = 1>
 int launch_nn_q16_t(icp_handle* h, long long n_q)
 {
-    auto kern = k_nn_bruteforce_q16<R, STAGES, CH, MIX, MINB>;
+    auto kern = k_nn_bruteforce_q16<R, STAGES, CH, MIX, MINB, false>;
+    auto kern_gated = k_nn_bruteforce_q16<R, STAGES, CH, MIX, MINB, true>;
     const size_t smem = (size_t)STAGES * ((Q16_TILE_BYTES + 127) / 128 * 128) + 2 * STAGES * sizeof(uint64_t);
     { int rc_ = configure_smem(h, kern, smem); if (rc_) return rc_; }
+    { int rc_ = configure_smem(h, kern_gated, smem); if (rc_) return rc_; }
     const long long qb = (n_q + (long long)NN_THREADS * R - 1) / ((long long)NN_THREADS * R);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_THREADS, smem);
@@ -1336,10 +1345,70 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
     if (gy > 65535) { gy = 65535; tiles_per_cta = (int)((h->n_tiles + gy - 1) / gy); gy = (h->n_tiles + tiles_per_cta - 1) / tiles_per_cta; }
     dim3 grid((unsigned)qb, (unsigned)gy);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
-    kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_q16_tiles, h->d_q16_etiles, h->q16_axes, h->n_tiles, tiles_per_cta,
-                                                qx, qy, qz, n_q, h->d_keys, h->bound_active ? h->d_bound : nullptr,
-                                                (uint32_t)h->base_off, &h->d_state->converged);
+    const float* bound = h->bound_active ? h->d_bound : nullptr;
+    // slots in class order (nn_variant 77: identity, the A/B of this step)
+    const uint32_t* perm = nullptr;
+    if (h->prm.nn_variant != 77) {
+        size_t temp_bytes = 0;
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned char*)nullptr, (unsigned char*)nullptr,
+                                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_q, 0, Q16_CLASS_BITS, h->stream));
+        if (n_q > h->q16_class_capacity || temp_bytes > h->q16_sort_temp_bytes || !h->d_q16_hist) {
+            for (void* p : {(void*)h->d_q16_cls, (void*)h->d_q16_ids, (void*)h->d_q16_sort_temp}) if (p) cudaFree(p);
+            h->d_q16_cls = nullptr; h->d_q16_ids = nullptr; h->d_q16_sort_temp = nullptr;
+            h->q16_class_capacity = 0; h->q16_sort_temp_bytes = 0;
+            CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_cls, (size_t)n_q * 2));
+            CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_ids, (size_t)n_q * 2 * sizeof(uint32_t)));
+            CUDA_TRY(h, cudaMalloc(&h->d_q16_sort_temp, temp_bytes ? temp_bytes : 1));
+            if (!h->d_q16_hist) {
+                CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_hist, 258 * sizeof(unsigned int)));
+                CUDA_TRY(h, cudaMemsetAsync(h->d_q16_hist, 0, 258 * sizeof(unsigned int), h->stream));
+            }
+            h->q16_class_capacity = n_q; h->q16_sort_temp_bytes = temp_bytes;
+        }
+        const int* stop = &h->d_state->converged;
+        const int hg = (int)std::min<long long>((n_q + 255) / 256, (long long)h->sm_count * 8);
+        k_q16_class_hist<<<hg, 256, 0, h->stream>>>(h->d_keys, bound, n_q, h->d_q16_hist, stop);
+        k_q16_class_pick<<<1, 256, 0, h->stream>>>(h->d_q16_hist, n_q, stop);
+        k_q16_class_keys<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_keys, bound, n_q, h->d_q16_hist, h->d_q16_cls,
+                                                                              h->d_q16_ids, stop);
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->d_q16_sort_temp, temp_bytes, (const unsigned char*)h->d_q16_cls,
+                                                    h->d_q16_cls + h->q16_class_capacity, (const uint32_t*)h->d_q16_ids,
+                                                    h->d_q16_ids + h->q16_class_capacity, (int)n_q, 0, Q16_CLASS_BITS, h->stream));
+        perm = h->d_q16_ids + h->q16_class_capacity;
+        h->launches += 6;
+    }
+    // classes >= hard_class go to the expansion-filter kernel (flat cost per pair, no pruning to lose)
+    static const int hard_env = getenv("ICP_Q16_HARD_CLASS") ? atoi(getenv("ICP_Q16_HARD_CLASS")) : Q16_HARD_CLASS;
+    const int hard_class = (perm != nullptr && h->prm.nn_variant != 78) ? hard_env : (1 << Q16_CLASS_BITS);
+    const bool gated = perm != nullptr && hard_class < (1 << Q16_CLASS_BITS);
+    const unsigned int* first_hard = h->d_q16_hist ? h->d_q16_hist + 257 : nullptr;
+    if (gated) {
+        k_q16_class_first<<<1, 32, 0, h->stream>>>(h->d_q16_cls + h->q16_class_capacity, n_q, hard_class, h->d_q16_hist,
+                                                   &h->d_state->converged);
+        h->launches++;
+    }
+    (gated ? kern_gated : kern)<<<grid, NN_THREADS, smem, h->stream>>>(
+        h->d_q16_tiles, h->d_q16_etiles, h->q16_axes, h->n_tiles, tiles_per_cta, qx, qy, qz, n_q, h->d_keys, bound,
+        (uint32_t)h->base_off, &h->d_state->converged, perm, first_hard);
     h->launches++;
+    if (gated) {
+        auto fk = k_nn_bruteforce_filter<4, 3, true>;
+        const size_t fsmem = (size_t)3 * NNF_TILE_BYTES + 3 * sizeof(uint64_t);
+        { int rc_ = configure_smem(h, fk, fsmem); if (rc_) return rc_; }
+        const long long fqb = (n_q + (long long)NN_THREADS * 4 - 1) / ((long long)NN_THREADS * 4);
+        int focc = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, fk, NN_THREADS, fsmem);
+        const long long fslots = (long long)h->sm_count * std::max(1, focc);
+        // how many hard blocks there are is only known on the device (see the kernel): split the base finely
+        (void)fslots;
+        long long fgy = std::max<long long>(1, std::min<long long>(32, h->n_tiles / 4));
+        int ftiles = (int)((h->n_tiles + fgy - 1) / fgy);
+        fgy = (h->n_tiles + ftiles - 1) / ftiles;
+        fk<<<dim3((unsigned)fqb, (unsigned)fgy), NN_THREADS, fsmem, h->stream>>>(
+            h->d_filter_tiles, h->d_base_tiles, h->d_filter_info, h->n_tiles, ftiles, qx, qy, qz, n_q, h->d_keys,
+            (uint32_t)h->base_off, 1, &h->d_state->converged, perm, first_hard);
+        h->launches++;
+    }
     CUDA_TRY(h, cudaGetLastError());
     return ICP_OK;
 }
@@ -1376,6 +1445,10 @@ int launch_nn(icp_handle* h, long long n_q)
     if (q16_variant(variant)) {
         int rc = build_q16(h, (variant == 54 || variant == 55 || variant == 66) ? 1 : 0);
         if (rc) return rc;
+        if (variant != 77 && variant != 78) {       // the hard classes of the slots are served by the expansion-filter kernel
+            rc = build_filter(h);
+            if (rc) return rc;
+        }
     }
     if (variant >= 20 && variant <= 29) {
         int rc = build_filter(h);      // outside the profiled region (one-time)
@@ -1415,6 +1488,8 @@ int launch_nn(icp_handle* h, long long n_q)
         case 71: return launch_nn_q16_t<4, 8, 128, 3, 3>(h, n_q);      // 62 with an 8-tile ring
         case 72: return launch_nn_q16_t<4, 8, 128, 5, 3>(h, n_q);      // 70 with an 8-tile ring
         case 73: return launch_nn_q16_t<4, 8, 256, 5, 3>(h, n_q);      // 72 with 256-vertex chunks
+        case 77: return launch_nn_q16_t<4, 8, 128, 3, 3>(h, n_q);      // 71 without the class order of the slots (A/B)
+        case 78: return launch_nn_q16_t<4, 8, 128, 3, 3>(h, n_q);      // 71 with the class order, every class in the q16 kernel (A/B)
         case 68: return launch_nn_q16_t<8, 4, 128, 3>(h, n_q);
         case 69: return launch_nn_q16_t<2, 4, 128, 3, 3>(h, n_q);
         case 40: return launch_nn_slab_t<4, 3, 32>(h, n_q);
@@ -2193,7 +2268,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound, h->d_tt_boxes, h->d_tt_tiles, h->d_tt_desc, h->d_tt_queue, h->d_win_tile, h->d_tt_part, h->d_tt_tickets};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound, h->d_tt_boxes, h->d_tt_tiles, h->d_tt_desc, h->d_tt_queue, h->d_win_tile, h->d_tt_part, h->d_tt_tickets, h->d_q16_cls, h->d_q16_ids, h->d_q16_hist, h->d_q16_sort_temp};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }

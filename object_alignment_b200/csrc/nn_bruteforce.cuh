@@ -297,16 +297,28 @@ __global__ void k_build_filter_tiles(const float4* __restrict__ base4, long long
     t[0] = x; t[NN_TILE] = y; t[2 * NN_TILE] = z; t[3 * NN_TILE] = bn;
 }
 
-template <int R, int STAGES>
+template <int R, int STAGES, bool GATED = false>
 __global__ void __launch_bounds__(NN_THREADS)
 k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict__ base_tiles,
                        const FilterInfo* __restrict__ info, int n_tiles, int tiles_per_cta,
                        const float* __restrict__ qx, const float* __restrict__ qy,
                        const float* __restrict__ qz, long long n_queries,
                        unsigned long long* __restrict__ keys, uint32_t index_offset, int seeded,
-                       const int* __restrict__ stop_flag)
+                       const int* __restrict__ stop_flag, const uint32_t* __restrict__ perm,
+                       const unsigned int* __restrict__ first_hard)
 {
+    // GATED: perm = the slots in class order (see "query classes" in nn_bruteforce_q16.cuh), *first_hard = the
+    // first position of a HARD class.  The launch then serves only the positions from there on -- the queries
+    // whose pruning radius is so large that the q16 kernel's slow path would cost more than this kernel's flat
+    // 3 FFMA2 + 1 FMNMX3 per two pairs.  How many there are is only known on the device: blockIdx.x counts
+    // blocks of hard positions, the CTAs beyond the last one leave at once, and grid.y splits the base finely
+    // so that even a handful of hard blocks fill the machine.
     if (stop_flag != nullptr && *stop_flag != 0) return;
+    long long first = 0;                      // GATED: the first position this launch serves
+    if (GATED) {
+        first = (long long)*first_hard;
+        if (first + (long long)blockIdx.x * (NN_THREADS * R) >= n_queries) return;     // blockIdx.x counts HARD blocks
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * NNF_TILE_BYTES);
@@ -333,14 +345,17 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
 
     const float inf = __int_as_float(0x7f800000);
     const float cx = info->cx, cy = info->cy, cz = info->cz, bmax = info->bmax;
-    const long long q0 = (long long)blockIdx.x * (NN_THREADS * R) + tid;
+    const long long q0 = first + (long long)blockIdx.x * (NN_THREADS * R) + tid;
     uint64_t nqx[R], nqy[R], nqz[R];          // (-2 q') broadcast into both halves
     float be[R], bed[R], delta[R];
     unsigned long long bkey[R];
+    uint32_t slot_of[R];                      // GATED: the slot behind this position, 0xFFFFFFFF = not served by this launch
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const long long p = q0 + (long long)r * NN_THREADS;
-        const bool ok = p < n_queries;
+        const long long i = q0 + (long long)r * NN_THREADS;
+        const bool ok = i < n_queries;
+        const long long p = ok ? (GATED ? (long long)perm[i] : i) : 0;
+        slot_of[r] = (GATED && ok) ? (uint32_t)p : 0xFFFFFFFFu;
         const float px = __fsub_rn(ok ? qx[p] : cx, cx), py = __fsub_rn(ok ? qy[p] : cy, cy),
                     pz = __fsub_rn(ok ? qz[p] : cz, cz);
         const float ax = -2.0f * px, ay = -2.0f * py, az = -2.0f * pz;
@@ -349,6 +364,7 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
         const float s = nq + bmax;
         delta[r] = 2.0e-6f * s * s;
         be[r] = inf; bed[r] = inf;
+        if (GATED && !ok) { be[r] = -inf; bed[r] = -inf; }      // a position of another class never triggers
         bkey[r] = KEY_NONE;
         if (seeded && ok) {
             // keys[p] already names a real vertex j of THIS shard (K1 re-evaluated the previous
@@ -409,8 +425,8 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (!(cm[r] <= bed[r])) continue;
-                    const long long p = q0 + (long long)r * NN_THREADS;
-                    if (p < n_queries) {
+                    const long long p = GATED ? (long long)slot_of[r] : q0 + (long long)r * NN_THREADS;
+                    if (GATED ? slot_of[r] != 0xFFFFFFFFu : p < n_queries) {
                         const float thr = fminf(be[r], cm[r]) + delta[r];
                         float ax, ay, az, dummy;
                         unpk2(nqx[r], ax, dummy); unpk2(nqy[r], ay, dummy); unpk2(nqz[r], az, dummy);
@@ -445,8 +461,8 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const long long p = q0 + (long long)r * NN_THREADS;
-        if (p < n_queries && bkey[r] != KEY_NONE) atomicMin(&keys[p], bkey[r]);
+        const long long p = GATED ? (long long)slot_of[r] : q0 + (long long)r * NN_THREADS;
+        if ((GATED ? slot_of[r] != 0xFFFFFFFFu : p < n_queries) && bkey[r] != KEY_NONE) atomicMin(&keys[p], bkey[r]);
     }
 }
 

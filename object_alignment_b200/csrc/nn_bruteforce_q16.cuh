@@ -38,17 +38,19 @@
 namespace icp {
 
 constexpr int Q16_PLANE_WORDS = NN_TILE / 2;                  // two vertices per word
-constexpr int Q16_HDR_WORDS = 8;
+constexpr int Q16_HDR_WORDS = 12;
 constexpr int Q16_TILE_WORDS = 3 * Q16_PLANE_WORDS + Q16_HDR_WORDS;   // a | b | c planes + header
-constexpr int Q16_TILE_BYTES = Q16_TILE_WORDS * 4;            // 6176 B per TMA bulk copy
+constexpr int Q16_TILE_BYTES = Q16_TILE_WORDS * 4;            // 6192 B per TMA bulk copy
 constexpr int Q16_WARPS = NN_THREADS / 32;
 constexpr float Q16_LEVELS = 65534.0f;                        // 65535 is the padding value (never inside)
 
-// header at the end of every tile (permuted axes a, b, c): lower corner, steps per unit, centre
+// header at the end of every tile (permuted axes a, b, c): lower corner, steps per unit, centre, upper corner
 struct Q16Hdr {
     float lo_a, lo_b, lo_c;
     float inv_a, inv_b, inv_c;
     float cen_a, cen_b;
+    float hi_a, hi_b, hi_c;       // with lo: the exact bounding box of the tile's finite vertices (the tile-level cull)
+    float pad;
 };
 static_assert(sizeof(Q16Hdr) == Q16_HDR_WORDS * 4, "Q16Hdr layout");
 
@@ -120,6 +122,8 @@ k_build_q16_tiles(const float4* __restrict__ base4, const uint32_t* __restrict__
     hd.inv_a = inv_p[0]; hd.inv_b = inv_p[1]; hd.inv_c = inv_p[2];
     hd.cen_a = 0.5f * box[axis_a] + 0.5f * box[3 + axis_a];
     hd.cen_b = 0.5f * box[axis_b] + 0.5f * box[3 + axis_b];
+    hd.hi_a = box[3 + axis_a]; hd.hi_b = box[3 + axis_b]; hd.hi_c = box[3 + axis_c];
+    hd.pad = 0.0f;
     float* et = etiles + t * CYL_TILE_FLOATS;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -281,6 +285,88 @@ __device__ __noinline__ unsigned long long q16_recheck(const uint32_t* tile, int
     return bkey;
 }
 
+// ---- query classes ---------------------------------------------------------------------------------------
+// The hot loop costs the same for every query, the slow path does not: a query whose pruning radius T is
+// large (an outlier of the moving cloud, a part of the scan the base does not cover) has a slab that crosses
+// a large share of ALL chunks, and since a warp runs the slow path whenever ANY of its lanes triggers, a few
+// such queries per warp make the whole warp slow (C5, 25 % uniform outliers spread over every warp: 2369 ms
+// per pass against 432 ms at the no-outlier rate).  So the pass walks the slots through a permutation that
+// groups queries of similar radius: class 0 = squared radius up to ~8x the median's power of two, then one
+// class per factor 4; the order inside a class stays the Morton order of the slots (stable sort), so a warp's
+// queries are still neighbours.  Easy warps run at full speed, hard warps run their slow path with all lanes.
+constexpr int Q16_CLASS_BITS = 4;
+constexpr int Q16_HARD_CLASS = 3;                // classes >= this one (radius > ~11x the median's) go to the expansion-filter kernel
+
+__device__ __forceinline__ uint32_t q16_radius_exponent(const unsigned long long* __restrict__ keys,
+                                                        const float* __restrict__ bound, long long t)
+{
+    float d = key_d2(keys[t]);                       // KEY_NONE decodes as NaN bits: exponent 255, the last class
+    if (bound != nullptr) d = fminf(d, bound[t]);
+    return (__float_as_uint(d) >> 23) & 0xFFu;
+}
+__global__ void k_q16_class_hist(const unsigned long long* __restrict__ keys, const float* __restrict__ bound,
+                                 long long n, unsigned int* __restrict__ hist, const int* __restrict__ stop_flag)
+{
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    __shared__ unsigned int sh[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&sh[q16_radius_exponent(keys, bound, t)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// hist[256] <- the exponent bin that holds the median; the histogram itself is zeroed for the next pass
+__global__ void k_q16_class_pick(unsigned int* __restrict__ hist, long long n, const int* __restrict__ stop_flag)
+{
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        int m = 255;
+        for (int i = 0; i < 256; ++i) {
+            acc += hist[i];
+            if (2 * acc >= n) { m = i; break; }
+        }
+        hist[256] = (unsigned int)m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+}
+__global__ void k_q16_class_keys(const unsigned long long* __restrict__ keys, const float* __restrict__ bound,
+                                 long long n, const unsigned int* __restrict__ hist, unsigned char* __restrict__ cls,
+                                 uint32_t* __restrict__ ids, const int* __restrict__ stop_flag)
+{
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int e = (int)q16_radius_exponent(keys, bound, t), m = (int)hist[256];
+    const int c = e <= m + 2 ? 0 : min((1 << Q16_CLASS_BITS) - 1, (e - m - 1) / 2);
+    cls[t] = (unsigned char)c;
+    ids[t] = (uint32_t)t;
+}
+// hist[257] <- the first position (in class order) that goes to the expansion-filter launch.  Which classes do is
+// decided here, from the populations: when more than a tenth of the queries lie above class 0 the cloud has
+// outliers (or overlaps the base only in part) and everything above class 0 is cheaper in the flat-cost kernel
+// (C5: 824 ms against 1093 ms per pass); otherwise only classes >= hard_class go there -- the thin upper tail of
+// an ordinary cloud is cheaper in the q16 kernel (C3: 29.2 ms against 32.4 ms).
+__global__ void k_q16_class_first(const unsigned char* __restrict__ cls_sorted, long long n, int hard_class,
+                                  unsigned int* __restrict__ hist, const int* __restrict__ stop_flag)
+{
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    auto first_of = [&](int c) {
+        long long lo = 0, hi = n;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if ((int)cls_sorted[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const long long f1 = first_of(1);
+    hist[257] = (unsigned int)((n - f1) * 10 > n ? f1 : first_of(hard_class));
+}
+
 // grid.x = query blocks of NN_THREADS * R slots, grid.y = base ranges of tiles_per_cta tiles.
 // Dynamic shared memory: STAGES * Q16_TILE_BYTES + 2 * STAGES * 8 (full / empty mbarriers).
 // `bound` (nullable): per-slot squared pruning radius from another source than the seed (the global
@@ -289,15 +375,23 @@ __device__ __noinline__ unsigned long long q16_recheck(const uint32_t* tile, int
 // MIX >= 1: the packed add moves (partly) to the fma pipe as IMAD and VIMNMX3.U16x2 folds two sums per
 //          instruction; both are 2-cycle instructions on 16-lane pipes (IMAD runs on fmaheavy only), so the
 //          mixes differ in how they balance alu / fmaheavy / issue slots -- see the loop body.
-template <int R, int STAGES, int CH, int MIX, int MINB>
+template <int R, int STAGES, int CH, int MIX, int MINB, bool GATED = false>
 __global__ void __launch_bounds__(NN_THREADS, MINB)
 k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict__ etiles, int axes,
                     int n_tiles, int tiles_per_cta, const float* __restrict__ qx,
                     const float* __restrict__ qy, const float* __restrict__ qz, long long n_queries,
                     unsigned long long* __restrict__ keys, const float* __restrict__ bound,
-                    uint32_t index_offset, const int* __restrict__ stop_flag)
+                    uint32_t index_offset, const int* __restrict__ stop_flag, const uint32_t* __restrict__ perm,
+                    const unsigned int* __restrict__ first_hard)
 {
+    // GATED: *first_hard = the first position that belongs to the expansion-filter launch that follows
+    // (k_nn_bruteforce_filter<.., true>: the classes with a large pruning radius); a CTA that holds only those leaves at once
     if (stop_flag != nullptr && *stop_flag != 0) return;
+    const long long n_mine = GATED ? (long long)*first_hard : n_queries;
+    // Positions are in class order, easy first; the query blocks are taken from the END: a block of hard
+    // queries takes many times longer than an easy one, and the blocks that start last set the tail of the launch.
+    const long long qblock = (perm != nullptr) ? (long long)(gridDim.x - 1 - blockIdx.x) : (long long)blockIdx.x;
+    if (GATED && qblock * (NN_THREADS * R) >= n_mine) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TILE_STRIDE = (Q16_TILE_BYTES + 127) / 128 * 128;      // 6272: keeps every slot 128-B aligned
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE_STRIDE);
@@ -326,13 +420,14 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
     const int axis_a = axes & 3, axis_b = (axes >> 2) & 3, axis_c = (axes >> 4) & 3;
     // R CONSECUTIVE slots per thread: slots are in Morton order of the moving vertices, so a warp's
     // 32 R queries form one compact patch and one slab axis per (warp, tile) suits all of them
-    const long long q0 = (long long)blockIdx.x * (NN_THREADS * R) + (long long)tid * R;
+    const long long q0 = qblock * (NN_THREADS * R) + (long long)tid * R;
     float qa[R], qb[R], qc[R], bnd[R], rad[R];      // bnd: squared pruning radius, rad: its root (< 0: padding slot)
     unsigned long long bkey[R];
+    // `perm` (nullable = identity): the slots in class order (see "query classes" above)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const long long p = q0 + r;
-        const bool ok = p < n_queries;
+        const bool ok = q0 + r < n_mine;
+        const long long p = ok ? (perm != nullptr ? (long long)perm[q0 + r] : q0 + r) : 0;
         const float x = ok ? qx[p] : 0.0f, y = ok ? qy[p] : 0.0f, z = ok ? qz[p] : 0.0f;
         qa[r] = axis_of(x, y, z, axis_a); qb[r] = axis_of(x, y, z, axis_b); qc[r] = axis_of(x, y, z, axis_c);
         bkey[r] = KEY_NONE;
@@ -357,8 +452,18 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
         const float lo_s = use_b ? hd.lo_b : hd.lo_a, inv_s = use_b ? hd.inv_b : hd.inv_a;
         uint32_t nlo[R], wp[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r) {
             q16_setup<MIX != 0>(use_b ? qb[r] : qa[r], rad[r], lo_s, inv_s, nlo[r], wp[r]);
+            // Tile-level cull on all three axes: a vertex can beat or tie only if it is within T of the query on
+            // EVERY axis, so a tile whose bounding box misses the query's box on any axis cannot trigger at all.
+            // Without it a query triggers in every tile that overlaps its slab along the ONE slab axis -- a whole
+            // cross-section of the object -- and the slow path sorts that out chunk by chunk (stage 1 / 2).
+            // 1.000001 T covers the rounding of the two differences; a NaN compares false (no cull).
+            const float tm = rad[r] * 1.000001f;
+            const bool miss = (qa[r] - hd.hi_a > tm) || (hd.lo_a - qa[r] > tm) || (qb[r] - hd.hi_b > tm) ||
+                              (hd.lo_b - qb[r] > tm) || (qc[r] - hd.hi_c > tm) || (hd.lo_c - qc[r] > tm);
+            if (miss) wp[r] = 0u;
+        }
         const uint4* plane = reinterpret_cast<const uint4*>(tile + (use_b ? Q16_PLANE_WORDS : 0));
 #pragma unroll 1
         for (int c = 0; c < NN_TILE / CH; ++c) {
@@ -456,8 +561,10 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const long long p = q0 + r;
-        if (p < n_queries && bkey[r] != KEY_NONE) atomicMin(&keys[p], bkey[r]);
+        if (q0 + r < n_mine && bkey[r] != KEY_NONE) {
+            const long long p = perm != nullptr ? (long long)perm[q0 + r] : q0 + r;
+            atomicMin(&keys[p], bkey[r]);
+        }
     }
 }
 

@@ -198,6 +198,45 @@ def test_q16_interval_never_misses_a_vertex_that_ties_the_best(kind, scale, offs
         # correctness; it may only cost a false positive, which the exact metric rejects (coordinates +inf)
 
 
+@pytest.mark.parametrize("kind", ["blob", "flat", "needle", "lattice"])
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1.0, 800.0), (1e-4, 0.0), (1e-4, 0.3), (1e3, -5e4)])
+def test_q16_tile_cull_never_drops_a_tile_that_holds_a_tie_of_the_best(kind, scale, offset):
+    """The tile-level cull of k_nn_bruteforce_q16 (fp32, the kernel's operation order): a tile is skipped for a
+    query when the tile's exact bounding box misses [q - T, q + T] on ANY axis, T = sqrt(best)(1 + 1e-6)(1 + 1e-6).
+    Property: a tile that holds a vertex j with S4(q, b_j) == best is never skipped -- and the cull is not
+    vacuous: with half the radius it does drop such tiles."""
+    rng = np.random.default_rng(zlib.crc32(repr(("q16cull", kind, scale, offset)).encode()))
+    pts = _tile(rng, kind, scale, np.array([offset, -0.6 * offset, 0.3 * offset]))
+    cen = pts.mean(axis=0)
+    ext = float(np.abs(pts - cen).max())
+    q = np.concatenate([
+        pts[rng.integers(0, len(pts), 48)] + rng.standard_normal((48, 3)) * 0.01 * ext,
+        cen + rng.standard_normal((48, 3)) * ext,
+        cen + rng.standard_normal((48, 3)) * 30 * ext,
+    ]).astype(F)
+    nq, nv = q.shape[0], pts.shape[0]
+    best = s4_d2(np.broadcast_to(q[:, None, :], (nq, nv, 3)), np.broadcast_to(pts[None], (nq, nv, 3)))
+
+    def missed(tm, lo, hi):
+        m = np.zeros(tm.shape, bool)
+        for a in range(3):
+            qa = q[:, None, a]
+            m |= ((qa - hi[a]).astype(F) > tm) | ((lo[a] - qa).astype(F) > tm)
+        return m
+
+    # sub-tiles of 8 vertices each: every vertex is the "best" once, its own sub-tile must survive
+    order = np.argsort(pts[:, 0], kind="stable")
+    for g in range(0, nv, 64):
+        sel = order[g:g + 8]
+        lo, hi = pts[sel].min(axis=0), pts[sel].max(axis=0)
+        T = (np.sqrt(best[:, sel]).astype(F) * F(1.000001)).astype(F)      # q16_radius
+        assert not missed((T * F(1.000001)).astype(F), lo, hi).any()
+    far = cen + np.array([40 * ext, 0, 0])
+    lo, hi = (pts + far).astype(F).min(axis=0), (pts + far).astype(F).max(axis=0)
+    T = (np.sqrt(best.min(axis=1, keepdims=True)).astype(F) * F(1.000001)).astype(F)
+    assert missed((T * F(1.000001)).astype(F), lo, hi)[:96].all()         # a tile far beyond the radius is dropped
+
+
 def test_q16_filter_actually_prunes():
     """Not vacuous: far vertices are outside the interval, and a radius that is too small loses vertices."""
     rng = np.random.default_rng(9)
