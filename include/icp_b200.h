@@ -73,12 +73,18 @@ typedef struct icp_params {
     int32_t world_size;      /* number of base shards / GPUs (1 when single GPU)                 */
     int32_t nn_variant;      /* kernel variant for tuning / A-B runs; 0 = library default.  Every variant
                                 returns the same keys.  Brute force: 1-6 direct metric, 20-24 expansion
-                                filter, 30-36 cylinder filter, 40-45 slab filter (default for seeded
-                                passes until round 2), 50-57 / 60-69 16-bit quantised slab test (alu-only /
-                                split fma+alu loops; default for seeded passes: 71).  Tree (ICP_NN_BVH): default = warp walk over a 32-ary tree of Morton tiles; 12 = binary LBVH
-                                packet walk, 10 per-thread walk, 11 packet walk without the fused
-                                epilogue.  Surface: 10 per-thread walk, 11 packet walk with eager
-                                triangle tests (default: deferred tests)                          */
+                                filter, 30-36 cylinder filter, 40-45 slab filter (round-1 default), 50-57 /
+                                60-73 16-bit quantised slab test (alu-only / split fma+alu loops; default for
+                                seeded passes: 71, slots walked in class order with the hard classes served by
+                                the expansion-filter kernel; 77 = 71 in plain slot order, 78 = 71 in class order
+                                with every class in the q16 kernel, 58 = without the global pruning bound, 79 = greedy
+                                tile-tree seeds for the cold pass instead of the exact tree search, 59 =
+                                cold pass by the expansion filter instead of tile-tree seeds).
+                                Tree (ICP_NN_BVH): default = persistent warp walk over a 32-ary tree of Morton
+                                tiles, the whole iteration in one launch; 13 = its first generation (one CTA per
+                                128 slots), 12 = binary LBVH packet walk, 10 per-thread walk, 11 packet walk
+                                without the fused epilogue.  Surface: 10 per-thread walk, 11 packet walk with
+                                eager triangle tests (default: deferred tests)                          */
     int32_t shard_mode;      /* icp_shard_mode when world_size > 1                               */
 } icp_params;
 

@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <new>
 #include <vector>
@@ -829,6 +830,12 @@ struct icp_handle {
     TileTree* d_tt_desc = nullptr;
     TileTree tt{};
     bool tt_built = false;
+    // grow-only scratch for the temporaries of the index builds (codes, orders, sort space): cudaMalloc / cudaFree
+    // per build cost 4-140 ms of host time on a busy box, the kernels of a build 3-5 ms
+    void* d_build_scratch = nullptr;
+    size_t build_scratch_bytes = 0;
+    long long bvh_sorted_cap = 0, bvh_nodes_cap = 0, tt_boxes_cap = 0, tt_tiles_cap = 0, q16_tiles_cap = 0, q16_etiles_cap = 0,
+              filter_tiles_cap = 0;
     // second-generation walk (k_nn_tiletree_p): batch queue, winner tiles per slot, ticket tree of moment partials
     TTQueue* d_tt_queue = nullptr;
     int* d_win_tile = nullptr;
@@ -940,6 +947,27 @@ int ensure(icp_handle* h, T*& ptr, long long& cap, long long need)
     return ICP_OK;
 }
 
+// carve-up of the build scratch: sizes first (need()), then one ensure, then take() in the same order
+struct BuildArena {
+    size_t total = 0, off = 0;
+    char* base = nullptr;
+    static size_t up(size_t v) { return (v + 255) / 256 * 256; }
+    void need(size_t bytes) { total += up(bytes ? bytes : 1); }
+    int commit(icp_handle* h)
+    {
+        if (total > h->build_scratch_bytes) {
+            if (h->d_build_scratch) cudaFree(h->d_build_scratch);
+            h->d_build_scratch = nullptr; h->build_scratch_bytes = 0;
+            CUDA_TRY(h, cudaMalloc(&h->d_build_scratch, total));
+            h->build_scratch_bytes = total;
+        }
+        base = (char*)h->d_build_scratch;
+        off = 0;
+        return ICP_OK;
+    }
+    template <typename T> T* take(size_t bytes) { T* p = (T*)(base + off); off += up(bytes ? bytes : 1); return p; }
+};
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember it per handle
 // (a handle is bound to one device), not per process.
 template <typename K>
@@ -981,6 +1009,21 @@ long long query_count(const icp_handle* h)
     const long long s = h->prm.stride > 1 ? h->prm.stride : 1;
     return (L + s - 1) / s;                       // len(vlist[0::s])
 }
+
+// ICP_TRACE_BUILD=1: wall-clock time of the one-time index builds to stderr (host side, includes the syncs)
+struct BuildTrace {
+    const char* what; icp_handle* h; bool on; std::chrono::steady_clock::time_point t0;
+    BuildTrace(icp_handle* h_, const char* w) : what(w), h(h_) {
+        static const bool enabled = getenv("ICP_TRACE_BUILD") != nullptr;
+        on = enabled;
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    ~BuildTrace() {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 0.05) fprintf(stderr, "[icp build] %-24s %8.3f ms\n", what, ms);
+    }
+};
 
 struct ProfScope {
     icp_handle* h; int which; EventPair* ep = nullptr;
@@ -1046,23 +1089,23 @@ int launch_nn_t(icp_handle* h, long long n_q)
 int build_filter(icp_handle* h)
 {
     if (h->filter_built) return ICP_OK;
-    if (h->d_filter_tiles) { cudaFree(h->d_filter_tiles); h->d_filter_tiles = nullptr; }
+    BuildTrace bt_(h, "build_filter");
     if (!h->d_filter_info) CUDA_TRY(h, cudaMalloc((void**)&h->d_filter_info, sizeof(FilterInfo)));
     const long long n = h->n_local, n_pad = (long long)h->n_tiles * NN_TILE;
     if (n > 0) {
-        float *part = nullptr, *bbox = nullptr;
         const int pb = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
-        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 24));
-        CUDA_TRY(h, cudaMalloc((void**)&bbox, 24));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_filter_tiles, (size_t)n_pad * 4 * sizeof(float)));
+        BuildArena ar;
+        ar.need((size_t)pb * 24); ar.need(24);
+        { int rc = ar.commit(h); if (rc) return rc; }
+        float* part = ar.take<float>((size_t)pb * 24);
+        float* bbox = ar.take<float>(24);
+        { int rc = ensure(h, h->d_filter_tiles, h->filter_tiles_cap, n_pad * 4); if (rc) return rc; }
         k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
         k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
         k_filter_info<<<1, 32, 0, h->stream>>>(bbox, h->d_filter_info);
         k_build_filter_tiles<<<(unsigned)((n_pad + 255) / 256), 256, 0, h->stream>>>(h->d_base4, n, n_pad, h->d_filter_info, h->d_filter_tiles);
         h->launches += 4;
         CUDA_TRY(h, cudaGetLastError());
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        cudaFree(part); cudaFree(bbox);
     }
     h->filter_built = true;
     return ICP_OK;
@@ -1270,30 +1313,30 @@ int launch_nn_slab_t(icp_handle* h, long long n_q)
 int build_q16(icp_handle* h, int want_order)
 {
     if (h->q16_order == want_order) return ICP_OK;
-    for (void* p : {(void*)h->d_q16_tiles, (void*)h->d_q16_etiles}) if (p) cudaFree(p);
-    h->d_q16_tiles = nullptr; h->d_q16_etiles = nullptr;
+    BuildTrace bt_(h, "build_q16");
     const long long n = h->n_local;
     if (n > 0) {
-        unsigned long long *codes = nullptr, *codes_out = nullptr;
-        uint32_t *order = nullptr, *order_out = nullptr;
-        float *part = nullptr, *bbox = nullptr;
-        void* temp = nullptr;
         size_t temp_bytes = 0;
         const int pb = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
         const unsigned gn = (unsigned)((n + 255) / 256);
-        CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 24));
-        CUDA_TRY(h, cudaMalloc((void**)&bbox, 24));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_tiles, (size_t)h->n_tiles * Q16_TILE_BYTES));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_etiles, (size_t)h->n_tiles * CYL_TILE_BYTES));
-        CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n * 8));
-        CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n * 8));
-        CUDA_TRY(h, cudaMalloc((void**)&order, (size_t)n * 4));
-        CUDA_TRY(h, cudaMalloc((void**)&order_out, (size_t)n * 4));
+        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                                    (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64, h->stream));
+        BuildArena ar;
+        ar.need((size_t)pb * 24); ar.need(24); ar.need((size_t)n * 8); ar.need((size_t)n * 8); ar.need((size_t)n * 4);
+        ar.need((size_t)n * 4); ar.need(temp_bytes);
+        { int rc = ar.commit(h); if (rc) return rc; }
+        float* part = ar.take<float>((size_t)pb * 24);
+        float* bbox = ar.take<float>(24);
+        unsigned long long* codes = ar.take<unsigned long long>((size_t)n * 8);
+        unsigned long long* codes_out = ar.take<unsigned long long>((size_t)n * 8);
+        uint32_t* order = ar.take<uint32_t>((size_t)n * 4);
+        uint32_t* order_out = ar.take<uint32_t>((size_t)n * 4);
+        void* temp = ar.take<char>(temp_bytes);
+        { int rc = ensure(h, h->d_q16_tiles, h->q16_tiles_cap, (long long)h->n_tiles * Q16_TILE_WORDS); if (rc) return rc; }
+        { int rc = ensure(h, h->d_q16_etiles, h->q16_etiles_cap, (long long)h->n_tiles * CYL_TILE_FLOATS); if (rc) return rc; }
         k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
         k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
         k_morton_codes<<<gn, 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order);
-        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 64, h->stream));
-        CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
         CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
         // a, b = the two longest axes of the shard (the candidate slab axes), c = the shortest
         float hb[6];
@@ -1315,8 +1358,6 @@ int build_q16(icp_handle* h, int want_order)
                                                                       h->d_q16_tiles, h->d_q16_etiles);
         h->launches += 7;
         CUDA_TRY(h, cudaGetLastError());
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        for (void* p : {(void*)codes, (void*)codes_out, (void*)order, (void*)order_out, (void*)part, (void*)bbox, temp}) if (p) cudaFree(p);
     }
     h->q16_order = want_order;
     return ICP_OK;
@@ -1416,28 +1457,41 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
 bool q16_variant(int v) { return v >= 50 && v <= 79; }   // 58 = 62 without the global pruning bound (A/B)
 
 int build_tiletree(icp_handle* h);
+int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused);
+template <bool FUSED> int launch_tiletree_walk(icp_handle* h, long long n_q, int solve);
 
 int launch_nn(icp_handle* h, long long n_q)
 {
     if (n_q <= 0 || h->n_tiles <= 0) return ICP_OK;
     int variant = h->prm.nn_variant;
-    // The q16 kernel needs a seed.  First pass of the default path: every query takes the nearest vertex
-    // of the Morton tile nearest to it (greedy descent of the tile tree, 0.1 ms) as its seed -- a real
-    // vertex, so the exhaustive seeded pass that follows is exact whatever the seed's quality.
-    // nn_variant 59: first pass by the unseeded expansion-filter kernel instead (round-1 behaviour).
+    // The q16 kernel needs a seed: any real vertex of the shard with its exact S4 distance -- the exhaustive
+    // pass that follows is exact whatever the seed's quality, a good one only makes it prune sooner.  First pass
+    // of the default path: the tile-tree search (the exact nearest vertex, 0.3-0.5 ms at C3).
+    // nn_variant 79: greedy descent of the tile tree instead (the nearest vertex of the nearest Morton tile);
+    // nn_variant 59: first pass by the unseeded expansion-filter kernel (round-1 behaviour).
     if ((variant == 0 || (q16_variant(variant) && variant != 59)) && !h->bf_warm_active && h->n_tiles >= 16) {
         int rc = build_tiletree(h);
         if (rc) return rc;
-        ProfScope ps(h, 3);
-        float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
-        k_tt_seed<<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_tt_desc, qx, qy, qz, n_q, h->d_keys,
-                                                                        (uint32_t)h->base_off, &h->d_state->converged);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
+        if (variant != 79 && uses_slots(h)) {
+            // the exact tree search as the seed (0.3-0.5 ms at C3): the exhaustive pass that follows then prunes
+            // with the true nearest distance from its first tile on (first iteration 126 -> ~30 ms at C3)
+            rc = ensure_tiletree_walk(h, n_q, false);
+            if (rc) return rc;
+            ProfScope ps(h, 3);
+            rc = launch_tiletree_walk<false>(h, n_q, 0);
+            if (rc) return rc;
+        } else {       // nn_variant 79: greedy descent only (round-2 first half)
+            ProfScope ps(h, 3);
+            float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
+            k_tt_seed<<<(unsigned)((n_q + 127) / 128), 128, 0, h->stream>>>(h->d_tt_desc, qx, qy, qz, n_q, h->d_keys,
+                                                                            (uint32_t)h->base_off, &h->d_state->converged);
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
+        }
         h->bf_warm_active = true;
     }
     if (q16_variant(variant) && !h->bf_warm_active) variant = 0;       // no seed (tiny shard / variant 59): cold pass below
-    if (variant == 59) variant = 71;
+    if (variant == 59 || variant == 79) variant = 71;
     if (variant == 0) {
         if (h->bf_warm_active && h->n_tiles >= 16) variant = 71;       // seeded: 16-bit slab kernel
         else variant = h->n_tiles >= 256 ? 20 : 2;                     // cold: filter / direct kernel
@@ -1521,35 +1575,34 @@ int launch_nn(icp_handle* h, long long n_q)
 int build_bvh(icp_handle* h)
 {
     if (h->bvh_built) return ICP_OK;
-    if (h->d_bvh_nodes) { cudaFree(h->d_bvh_nodes); h->d_bvh_nodes = nullptr; }
-    if (h->d_bvh_sorted) { cudaFree(h->d_bvh_sorted); h->d_bvh_sorted = nullptr; }
+    BuildTrace bt_(h, "build_bvh");
     const long long n = h->n_local;
     h->bvh_P = 0;
     if (n <= 0) { h->bvh_built = true; return ICP_OK; }
     const int n_runs = (int)((n + BVH_LEAF - 1) / BVH_LEAF);
     const long long n_pad = (long long)n_runs * BVH_LEAF;
-    unsigned long long *codes = nullptr, *codes_out = nullptr, *run_keys = nullptr;
-    uint32_t *order = nullptr, *order_out = nullptr;
-    int* leaf_parent = nullptr;
-    float *part = nullptr, *bbox = nullptr;
-    void* temp = nullptr;
     size_t temp_bytes = 0;
     const int pb = std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
-    CUDA_TRY(h, cudaMalloc((void**)&codes, (size_t)n * 8));
-    CUDA_TRY(h, cudaMalloc((void**)&codes_out, (size_t)n * 8));
-    CUDA_TRY(h, cudaMalloc((void**)&order, (size_t)n * 4));
-    CUDA_TRY(h, cudaMalloc((void**)&order_out, (size_t)n * 4));
-    CUDA_TRY(h, cudaMalloc((void**)&run_keys, (size_t)n_runs * 8));
-    CUDA_TRY(h, cudaMalloc((void**)&leaf_parent, (size_t)n_runs * 4));
-    CUDA_TRY(h, cudaMalloc((void**)&part, (size_t)pb * 6 * 4));
-    CUDA_TRY(h, cudaMalloc((void**)&bbox, 6 * 4));
-    CUDA_TRY(h, cudaMalloc((void**)&h->d_bvh_sorted, (size_t)n_pad * sizeof(float4)));
-    CUDA_TRY(h, cudaMalloc((void**)&h->d_bvh_nodes, (size_t)std::max(1, n_runs - 1) * sizeof(BvhNode)));
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                                (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 63, h->stream));
+    BuildArena ar;
+    ar.need((size_t)n * 8); ar.need((size_t)n * 8); ar.need((size_t)n * 4); ar.need((size_t)n * 4);
+    ar.need((size_t)n_runs * 8); ar.need((size_t)n_runs * 4); ar.need((size_t)pb * 24); ar.need(24); ar.need(temp_bytes);
+    { int rc = ar.commit(h); if (rc) return rc; }
+    unsigned long long* codes = ar.take<unsigned long long>((size_t)n * 8);
+    unsigned long long* codes_out = ar.take<unsigned long long>((size_t)n * 8);
+    uint32_t* order = ar.take<uint32_t>((size_t)n * 4);
+    uint32_t* order_out = ar.take<uint32_t>((size_t)n * 4);
+    unsigned long long* run_keys = ar.take<unsigned long long>((size_t)n_runs * 8);
+    int* leaf_parent = ar.take<int>((size_t)n_runs * 4);
+    float* part = ar.take<float>((size_t)pb * 24);
+    float* bbox = ar.take<float>(24);
+    void* temp = ar.take<char>(temp_bytes);
+    { int rc = ensure(h, h->d_bvh_sorted, h->bvh_sorted_cap, n_pad); if (rc) return rc; }
+    { int rc = ensure(h, h->d_bvh_nodes, h->bvh_nodes_cap, (long long)std::max(1, n_runs - 1)); if (rc) return rc; }
     k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
     k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
     k_morton_codes<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order);
-    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
-    CUDA_TRY(h, cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
     CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
     k_bvh_gather<<<(unsigned)((n_pad + 255) / 256), 256, 0, h->stream>>>(h->d_base4, order_out, n, n_pad, h->d_bvh_sorted);
     k_run_keys<<<(unsigned)((n_runs + 255) / 256), 256, 0, h->stream>>>(codes_out, n, n_runs, run_keys);
@@ -1559,10 +1612,6 @@ int build_bvh(icp_handle* h)
     }
     h->launches += 8;
     CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(codes); cudaFree(codes_out); cudaFree(order); cudaFree(order_out);
-    cudaFree(run_keys); cudaFree(leaf_parent);
-    cudaFree(part); cudaFree(bbox); cudaFree(temp);
     const int P = n_runs;
     h->bvh_P = P;
     h->bvh_built = true;
@@ -1573,10 +1622,9 @@ int build_bvh(icp_handle* h)
 int build_tiletree(icp_handle* h)
 {
     if (h->tt_built) return ICP_OK;
+    BuildTrace bt_(h, "build_tiletree(+bvh)");
     int rc = build_bvh(h);
     if (rc) return rc;
-    for (void* p : {(void*)h->d_tt_boxes, (void*)h->d_tt_tiles}) if (p) cudaFree(p);
-    h->d_tt_boxes = nullptr; h->d_tt_tiles = nullptr;
     memset(&h->tt, 0, sizeof(h->tt));
     const long long n = h->n_local;
     if (n > 0) {
@@ -1588,8 +1636,8 @@ int build_tiletree(icp_handle* h)
         }
         if (h->tt.count[levels - 1] > TT_FAN) return fail(h, ICP_ERR_BAD_ARG, "tile tree: too many vertices");
         h->tt.n_levels = levels;
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_boxes, (size_t)total * 2 * sizeof(float4)));
-        CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_tiles, (size_t)h->tt.count[0] * TT_TILE_FLOATS * sizeof(float)));
+        { int rc2 = ensure(h, h->d_tt_boxes, h->tt_boxes_cap, (long long)total * 2); if (rc2) return rc2; }
+        { int rc2 = ensure(h, h->d_tt_tiles, h->tt_tiles_cap, (long long)h->tt.count[0] * TT_TILE_FLOATS); if (rc2) return rc2; }
         k_tt_build_tiles<<<(unsigned)(((long long)h->tt.count[0] * 32 + 255) / 256), 256, 0, h->stream>>>(
             h->d_bvh_sorted, n, h->tt.count[0], h->d_tt_tiles, h->d_tt_boxes);
         for (int l = 1; l < levels; ++l)
@@ -1733,6 +1781,7 @@ int ensure_query_order(icp_handle* h, long long n_q)
         h->slots_stale = false;
         return ICP_OK;
     }
+    BuildTrace bt_(h, "query_order");
     h->slots_stale = false;
     h->warm_valid = false;
     if (n_q > h->order_capacity || !h->d_slot_pos) {
@@ -2268,7 +2317,7 @@ int icp_destroy(icp_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_base_tiles, h->d_base4, h->d_mov, h->d_vlist, h->d_q, h->d_keys, h->d_partials,
                     h->d_moments, h->d_hist, h->d_state, h->d_stats, h->d_flags, h->d_block_counts,
-                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound, h->d_tt_boxes, h->d_tt_tiles, h->d_tt_desc, h->d_tt_queue, h->d_win_tile, h->d_tt_part, h->d_tt_tickets, h->d_q16_cls, h->d_q16_ids, h->d_q16_hist, h->d_q16_sort_temp};
+                    h->d_total, h->d_pairs, h->d_v, h->d_scratch, h->d_bvh_nodes, h->d_bvh_sorted, h->d_slot_pos, h->d_pos_slot, h->d_mov_slots, h->d_order_scratch, h->d_filter_tiles, h->d_filter_info, h->d_tris4, h->d_tri_sorted, h->d_tri_nodes, h->d_keys_local, h->d_cyl_ftiles, h->d_cyl_etiles, h->d_cyl_hdrs, h->d_slab_ftiles, h->d_slab_etiles, h->d_slab_hdrs, h->d_partials2, h->d_q16_tiles, h->d_q16_etiles, h->d_bound, h->d_tt_boxes, h->d_tt_tiles, h->d_tt_desc, h->d_tt_queue, h->d_win_tile, h->d_tt_part, h->d_tt_tickets, h->d_q16_cls, h->d_q16_ids, h->d_q16_hist, h->d_q16_sort_temp, h->d_build_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int w = 0; w < 5; ++w)
         for (auto& e : h->ev_pool[w]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }

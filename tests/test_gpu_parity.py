@@ -494,7 +494,7 @@ def test_tree_modes_keep_slot_order_and_seeds_across_same_shape_uploads(mode):
 
 
 @pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36, 40, 41, 42, 44, 45, 50, 51, 52, 53, 54, 55, 56, 57,
-                                     58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73])
+                                     58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73, 77, 78, 79])
 def test_bruteforce_seeded_passes_stay_exact(variant):
     """From the second pass on the brute-force filter kernel starts its running minimum from the
     previous winner re-evaluated under the new pose.  Every pass must still return the oracle's
