@@ -84,7 +84,8 @@ typedef struct icp_params {
                                 tiles, the whole iteration in one launch; 13 = its first generation (one CTA per
                                 128 slots), 12 = binary LBVH packet walk, 10 per-thread walk, 11 packet walk
                                 without the fused epilogue.  Surface: 10 per-thread walk, 11 packet walk with
-                                eager triangle tests (default: deferred tests)                          */
+                                eager triangle tests, 14 deferred tests with separate reduce + solve launches
+                                (default: deferred tests, the whole iteration in one launch)            */
     int32_t shard_mode;      /* icp_shard_mode when world_size > 1                               */
 } icp_params;
 

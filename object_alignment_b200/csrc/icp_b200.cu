@@ -1457,7 +1457,7 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
 bool q16_variant(int v) { return v >= 50 && v <= 79; }   // 58 = 62 without the global pruning bound (A/B)
 
 int build_tiletree(icp_handle* h);
-int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused);
+int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused, long long entries = 0);
 template <bool FUSED> int launch_tiletree_walk(icp_handle* h, long long n_q, int solve);
 
 int launch_nn(icp_handle* h, long long n_q)
@@ -1662,7 +1662,8 @@ bool tiletree_variant(const icp_handle* h) { return h->prm.nn_variant == 0 || h-
 bool tiletree_persistent(const icp_handle* h) { return h->prm.nn_variant == 0; }   // 13 = first generation (one CTA per 128 slots)
 
 // queue, winner tiles and (fused) the ticket tree for n_q query slots; the persistent grid
-int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused)
+// `entries` (0 = one per batch of 32 slots): level-0 entries of the ticket tree (the surface walk: one per warp of its grid)
+int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused, long long entries)
 {
     if (!h->d_tt_queue) {
         CUDA_TRY(h, cudaMalloc((void**)&h->d_tt_queue, sizeof(TTQueue)));
@@ -1675,7 +1676,7 @@ int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused)
         CUDA_TRY(h, cudaMalloc((void**)&h->d_win_tile, (size_t)cap * sizeof(int)));
         h->win_tile_capacity = cap;
     }
-    const long long nb = (n_q + 31) / 32;
+    const long long nb = entries > 0 ? entries : (n_q + 31) / 32;
     if (fused && (nb != h->tt_tail_batches || !h->d_tt_part)) {
         TTTail& t = h->tt_tail;
         memset(&t, 0, sizeof(t));
@@ -1706,15 +1707,21 @@ int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused)
     return ICP_OK;
 }
 
+TTTail make_tail(const icp_handle* h, int solve)
+{
+    TTTail tail = h->tt_tail;
+    tail.part = h->d_tt_part; tail.tickets = h->d_tt_tickets; tail.moments = h->d_moments;
+    tail.stats = h->d_stats; tail.stats_capacity = h->stats_capacity;
+    tail.solve = solve; tail.scale_mode = h->prm.align_meth == 1; tail.use_target = h->prm.use_target; tail.target_d = h->prm.target_d;
+    return tail;
+}
+
 template <bool FUSED>
 int launch_tiletree_walk(icp_handle* h, long long n_q, int solve)
 {
     const long long nb = (n_q + 31) / 32;
     const int g = (int)std::max<long long>(1, std::min<long long>((nb + TT_THREADS / 32 - 1) / (TT_THREADS / 32), h->tt_grid));
-    TTTail tail = h->tt_tail;
-    tail.part = h->d_tt_part; tail.tickets = h->d_tt_tickets; tail.moments = h->d_moments;
-    tail.stats = h->d_stats; tail.stats_capacity = h->stats_capacity;
-    tail.solve = solve; tail.scale_mode = h->prm.align_meth == 1; tail.use_target = h->prm.use_target; tail.target_d = h->prm.target_d;
+    const TTTail tail = make_tail(h, solve);
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     const int warm = (h->warm_valid ? 1 : 0) | ((h->warm_valid && h->tt_win_valid) ? 2 : 0);
     k_nn_tiletree_p<FUSED><<<g, TT_THREADS, 0, h->stream>>>(
@@ -1976,7 +1983,7 @@ int launch_nn_surface(icp_handle* h, long long n_q)
     } else {                             // default: warp-packet walk, deferred (queued) triangle tests
         k_nn_surface_defer<false><<<g, SURF_THREADS, 0, h->stream>>>(
             h->d_tri_nodes, h->d_tri_sorted, h->tri_runs, qx, qy, qz, h->d_state, nullptr, nullptr, 0, 0, 0.0, 0,
-            n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent, nullptr);
+            n_q, h->d_keys, (uint32_t)h->base_off, h->tri_extent, nullptr, TTTail{});
     }
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -2035,6 +2042,12 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
         rc = ensure_tiletree_walk(h, n_q, true);
         if (rc) return rc;
     }
+    // surface walk (default variant): its warps feed the same ticket tree, the iteration is one launch as well
+    const bool surf_ticket = h->surface && h->prm.nn_variant != 11 && h->prm.nn_variant != 14 && h->n_local < (1ll << 27) && n_q > 0;
+    if (surf_ticket) {
+        rc = ensure_tiletree_walk(h, n_q, true, (long long)g * SURF_WARPS);
+        if (rc) return rc;
+    }
     if (h->pose_dirty) {
         ProfScope ps(h, 3);
         k_prepare_pose<<<1, 1, 0, h->stream>>>(h->d_state);
@@ -2073,11 +2086,16 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
                 h->d_tri_nodes, h->d_tri_sorted, h->n_local > 0 ? h->tri_runs : 0, nullptr, nullptr, nullptr, h->d_state,
                 h->d_mov_slots, h->d_tris4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
                 h->d_keys, (uint32_t)h->base_off, h->tri_extent, h->d_partials);
-        else if (h->surface)
+        else if (surf_ticket)
+            k_nn_surface_defer<true, true><<<g, SURF_THREADS, 0, h->stream>>>(
+                h->d_tri_nodes, h->d_tri_sorted, h->n_local > 0 ? h->tri_runs : 0, nullptr, nullptr, nullptr, h->d_state,
+                h->d_mov_slots, h->d_tris4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
+                h->d_keys, (uint32_t)h->base_off, h->tri_extent, nullptr, make_tail(h, h->prm.world_size == 1 ? 1 : 0));
+        else if (h->surface)        // nn_variant 14: walk + separate reduce and solve launches (A/B of the ticketed tail)
             k_nn_surface_defer<true><<<g, SURF_THREADS, 0, h->stream>>>(
                 h->d_tri_nodes, h->d_tri_sorted, h->n_local > 0 ? h->tri_runs : 0, nullptr, nullptr, nullptr, h->d_state,
                 h->d_mov_slots, h->d_tris4, h->base_off, h->n_local, h->prm.thresh, h->warm_valid ? 1 : 0, n_q,
-                h->d_keys, (uint32_t)h->base_off, h->tri_extent, h->d_partials);
+                h->d_keys, (uint32_t)h->base_off, h->tri_extent, h->d_partials, TTTail{});
         else if (tiletree)
             k_nn_tiletree<true><<<g, TT_THREADS, 0, h->stream>>>(
                 h->d_tt_desc, nullptr, nullptr, nullptr, h->d_state,
@@ -2092,6 +2110,22 @@ int enqueue_iteration_fused(icp_handle* h, long long n_q)
     }
     h->warm_valid = true;
     h->bf_warm_valid = false;
+    if (surf_ticket) {
+        if (h->prm.world_size > 1) {      // queries sharded: the only exchange is the 20-double moment sum
+            if (!h->comm) return fail(h, ICP_ERR_STATE, "world_size > 1 but icp_comm_init was not called");
+            {
+                ProfScope ps(h, 4);
+                NCCL_TRY(h, g_nccl.AllReduce(h->d_moments, h->d_moments, MOM, ncclDouble, ncclSum, h->comm, h->stream));
+            }
+            ProfScope ps(h, 2);
+            k_solve_update<<<1, 32, 0, h->stream>>>(h->d_state, h->d_moments, h->prm.align_meth == 1,
+                                                    h->prm.use_target, h->prm.target_d, h->d_stats,
+                                                    h->stats_capacity);
+            h->launches += 1;
+        }
+        CUDA_TRY(h, cudaGetLastError());
+        return ICP_OK;
+    }
     if (h->prm.world_size == 1 && g <= 16384) {      // one launch: reduce + solve + pose update
         ProfScope ps(h, 2);
         k_reduce_solve<<<1, MOM * 32, 0, h->stream>>>(h->d_state, h->d_partials, g, h->d_moments, h->prm.align_meth == 1,

@@ -403,16 +403,21 @@ k_nn_surface_packet(const BvhNode* __restrict__ nodes, const float4* __restrict_
 // ---------------------------------------------------------------------------------------------
 constexpr int SURF_QCAP = 32 + 32 * TRI_LEAF;     // queued pairs before a flush + one leaf's worth
 
-template <bool FUSED>
+// TICKET (with FUSED): the moment sums of every warp enter the ticket tree of nn_tiletree.cuh (`tail`; entry =
+// the warp's index in the grid) instead of per-CTA partials, and the warp that completes the top group runs the
+// solve and the pose update: the iteration is ONE launch, like the tile-tree walk's.
+template <bool FUSED, bool TICKET = false>
 __global__ void __launch_bounds__(SURF_BOUNDS, ICP_SURF_RESIDENT / SURF_BOUNDS)
 k_nn_surface_defer(const BvhNode* __restrict__ nodes, const float4* __restrict__ sorted, int n_runs,
                    const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
-                   const DevState* __restrict__ st, const float4* __restrict__ mov_slots,
+                   DevState* st, const float4* __restrict__ mov_slots,
                    const float4* __restrict__ tris4, long long base_off, long long n_local, double thresh,
                    int warm, long long n_queries, unsigned long long* __restrict__ keys,
-                   uint32_t index_offset, float coord_extent, double* __restrict__ partials)
+                   uint32_t index_offset, float coord_extent, double* __restrict__ partials,
+                   const __grid_constant__ TTTail tail)
 {
-    if (st->converged) return;
+    if (*reinterpret_cast<volatile int*>(&st->converged)) return;     // (this launch's own solve cannot have run yet: it waits for every warp's entry)
+    __shared__ double s_mom[TICKET ? SURF_WARPS : 1][MOM];
     __shared__ int s_ref[SURF_WARPS][BVH_STACK];
     __shared__ float s_bound[SURF_WARPS][BVH_STACK];
     __shared__ uint32_t s_queue[SURF_WARPS][SURF_QCAP];
@@ -572,7 +577,20 @@ k_nn_surface_defer(const BvhNode* __restrict__ nodes, const float4* __restrict__
                 keep = true;
             }
         }
-        fused_pair_moments<SURF_THREADS>(keep, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2], partials);
+        if (!TICKET) {
+            fused_pair_moments<SURF_THREADS>(keep, ax, ay, az, bx, by, bz, dist, st->shift[0], st->shift[1], st->shift[2], partials);
+        } else {
+            const double s0 = st->shift[0], s1 = st->shift[1], s2 = st->shift[2];
+            const double k = keep ? 1.0 : 0.0;
+            const double a0 = keep ? (double)ax - s0 : 0.0, a1 = keep ? (double)ay - s1 : 0.0, a2 = keep ? (double)az - s2 : 0.0;
+            const double b0 = keep ? (double)bx - s0 : 0.0, b1 = keep ? (double)by - s1 : 0.0, b2 = keep ? (double)bz - s2 : 0.0;
+            const double d = keep ? dist : 0.0;
+            double r0, r1, r2;
+            { const double v[8] = {k, a0, a1, a2, b0, b1, b2, b0 * a0}; r0 = warp_sum8(v, lane); }
+            { const double v[8] = {b0 * a1, b0 * a2, b1 * a0, b1 * a1, b1 * a2, b2 * a0, b2 * a1, b2 * a2}; r1 = warp_sum8(v, lane); }
+            { const double v[8] = {a0 * a0 + a1 * a1 + a2 * a2, b0 * b0 + b1 * b1 + b2 * b2, d, d * d, 0.0, 0.0, 0.0, 0.0}; r2 = warp_sum8(v, lane); }
+            tt_tail_push(tail, st, (unsigned)(blockIdx.x * SURF_WARPS + warp), r0, r1, r2, lane, s_mom[TICKET ? warp : 0]);
+        }
     }
 }
 

@@ -675,17 +675,17 @@ def test_surface_packet_walk_equals_per_thread_walk_and_fused_iteration():
     rng = np.random.default_rng(97)
     q[rng.choice(200_000, 2000, replace=False)] = ((rng.random((2000, 3)) - 0.5) * 5).astype(np.float32)  # outliers
     out = {}
-    for variant in (0, 11, 10):
+    for variant in (0, 14, 11, 10):
         with IcpEngine(nn_mode=2, thresh=0.5, use_target=False, nn_variant=variant) as e:
             e.set_base_triangles(tri)
             e.set_moving(q)
             e.set_matrices(np.eye(4), np.eye(4))
             idx, d2 = e.nn()
-            done, conv, recs = e.run(6)              # 0: fused deferred walk; 11: fused eager walk; 10: K1 + per-thread walk + K3/K4
+            done, conv, recs = e.run(6)              # 0: deferred walk, one launch per iteration (ticketed tail); 14: + separate reduce / solve; 11: fused eager walk; 10: K1 + per-thread walk + K3/K4
             idx_after, d2_after = e.nn()             # warm-started search under the final pose
             out[variant] = (idx, d2, [r.pairs for r in recs], e.matrix_world(), idx_after, d2_after)
     a, b = out[0], out[10]
-    for other in (out[11], out[10]):
+    for other in (out[14], out[11], out[10]):
         assert np.array_equal(a[0], other[0]) and np.array_equal(a[1].view(np.uint32), other[1].view(np.uint32))
         assert a[2] == other[2]
         np.testing.assert_allclose(a[3], other[3], atol=2e-6)
