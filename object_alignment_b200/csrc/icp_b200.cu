@@ -84,11 +84,20 @@ __global__ void k_transform_queries(const DevState* __restrict__ st, const float
                                     const unsigned long long* warm_src, const float4* __restrict__ base4,
                                     const float4* __restrict__ tris4, long long base_off,
                                     long long n_local, const unsigned long long* prev_global = nullptr,
-                                    float* __restrict__ bound_out = nullptr)
+                                    float* __restrict__ bound_out = nullptr, unsigned int* __restrict__ cls_scratch = nullptr,
+                                    int cls_pass = 0)
 {
+    // cls_scratch (nullable; launched with 256 threads then): the q16 kernel's class machinery -- this pass's
+    // exponent histogram of the pruning radii is accumulated here, where the seeds are made (nn_bruteforce_q16.cuh)
     if (st->converged) return;
+    __shared__ unsigned int s_hist[256];
+    if (cls_scratch != nullptr) {
+        s_hist[threadIdx.x & 255] = 0;
+        if (blockIdx.x == 0 && threadIdx.x < (1 << Q16_CLASS_BITS)) cls_scratch[Q16_CLS_COUNT + threadIdx.x] = 0;
+        __syncthreads();
+    }
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_q) return;
+    if (t < n_q) {
     const long long p = slot_pos ? (long long)slot_pos[t] : t;
     const long long vi = vlist ? (long long)vlist[p * stride] : p * stride;
     const float ax = mov[3 * vi], ay = mov[3 * vi + 1], az = mov[3 * vi + 2];
@@ -134,6 +143,14 @@ __global__ void k_transform_queries(const DevState* __restrict__ st, const float
         }
     }
     keys[t] = key;
+    if (cls_scratch != nullptr)
+        atomicAdd(&s_hist[q16_exponent_of(key, bound_out != nullptr ? bound_out[t] : __int_as_float(0x7f800000))], 1u);
+    }
+    if (cls_scratch != nullptr) {
+        __syncthreads();
+        const unsigned int c = s_hist[threadIdx.x & 255];
+        if (c) atomicAdd(&cls_scratch[Q16_CLS_EXP + 256 * (cls_pass & 1) + (threadIdx.x & 255)], c);
+    }
 }
 
 // Morton code of every sampled moving vertex (align-local space; a rigid pose keeps the order useful)
@@ -814,7 +831,9 @@ struct icp_handle {
     // q16 query classes: slots in class order (similar pruning radius together), rebuilt every pass
     unsigned char* d_q16_cls = nullptr;    // cls | cls_out
     uint32_t* d_q16_ids = nullptr;         // ids | perm
-    unsigned int* d_q16_hist = nullptr;    // 256 bins + the median bin
+    unsigned int* d_q16_hist = nullptr;    // Q16_CLS_WORDS: two exponent histograms (alternate passes) + the class populations
+    int q16_pass = 0;                      // parity selects the exponent histogram
+    bool q16_hist_by_k1 = false;           // K1 of the pass being enqueued has accumulated the histogram
     void* d_q16_sort_temp = nullptr;
     size_t q16_sort_temp_bytes = 0;
     long long q16_class_capacity = 0;
@@ -1134,7 +1153,7 @@ int launch_nn_filter_t(icp_handle* h, long long n_q)
     float* qx = h->d_q; float* qy = h->d_q + h->q_capacity; float* qz = h->d_q + 2 * h->q_capacity;
     kern<<<grid, NN_THREADS, smem, h->stream>>>(h->d_filter_tiles, h->d_base_tiles, h->d_filter_info, h->n_tiles,
                                                 tiles_per_cta, qx, qy, qz, n_q, h->d_keys, (uint32_t)h->base_off,
-                                                h->bf_warm_active ? 1 : 0, &h->d_state->converged, nullptr, nullptr);
+                                                h->bf_warm_active ? 1 : 0, &h->d_state->converged, nullptr, nullptr, 0);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return ICP_OK;
@@ -1363,6 +1382,40 @@ int build_q16(icp_handle* h, int want_order)
     return ICP_OK;
 }
 
+// The class machinery costs ~85 us per pass (one small kernel and a three-kernel radix sort), which a pass over
+// fewer than 2^18 slots does not earn back (C2, 100k x 100k: 0.73 -> 0.81 ms per iteration with it).
+// ICP_Q16_CLASS_MIN overrides the threshold (the tests run the class path on small clouds with it).
+bool q16_classes_wanted(const icp_handle* h, long long n_q)
+{
+    if (h->prm.nn_variant == 77) return false;
+    const char* e = getenv("ICP_Q16_CLASS_MIN");
+    const long long min_slots = e ? atoll(e) : (1ll << 18);
+    return n_q >= min_slots;
+}
+
+// buffers of the q16 class machinery for n_q slots
+int ensure_q16_classes(icp_handle* h, long long n_q)
+{
+    size_t temp_bytes = 0;
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned char*)nullptr, (unsigned char*)nullptr,
+                                                (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_q, 0, Q16_CLASS_BITS, h->stream));
+    if (!h->d_q16_hist) {
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_hist, Q16_CLS_WORDS * sizeof(unsigned int)));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_q16_hist, 0, Q16_CLS_WORDS * sizeof(unsigned int), h->stream));
+    }
+    if (n_q > h->q16_class_capacity || temp_bytes > h->q16_sort_temp_bytes) {
+        for (void* p : {(void*)h->d_q16_cls, (void*)h->d_q16_ids, (void*)h->d_q16_sort_temp}) if (p) cudaFree(p);
+        h->d_q16_cls = nullptr; h->d_q16_ids = nullptr; h->d_q16_sort_temp = nullptr;
+        h->q16_class_capacity = 0; h->q16_sort_temp_bytes = 0;
+        const long long cap = std::max<long long>(n_q, 1);
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_cls, (size_t)cap * 2));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_ids, (size_t)cap * 2 * sizeof(uint32_t)));
+        CUDA_TRY(h, cudaMalloc(&h->d_q16_sort_temp, temp_bytes ? temp_bytes : 1));
+        h->q16_class_capacity = cap; h->q16_sort_temp_bytes = temp_bytes;
+    }
+    return ICP_OK;
+}
+
 template <int R, int STAGES, int CH, int MIX, int MINB = 1>
 int launch_nn_q16_t(icp_handle* h, long long n_q)
 {
@@ -1389,48 +1442,33 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
     const float* bound = h->bound_active ? h->d_bound : nullptr;
     // slots in class order (nn_variant 77: identity, the A/B of this step)
     const uint32_t* perm = nullptr;
-    if (h->prm.nn_variant != 77) {
-        size_t temp_bytes = 0;
-        CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned char*)nullptr, (unsigned char*)nullptr,
-                                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_q, 0, Q16_CLASS_BITS, h->stream));
-        if (n_q > h->q16_class_capacity || temp_bytes > h->q16_sort_temp_bytes || !h->d_q16_hist) {
-            for (void* p : {(void*)h->d_q16_cls, (void*)h->d_q16_ids, (void*)h->d_q16_sort_temp}) if (p) cudaFree(p);
-            h->d_q16_cls = nullptr; h->d_q16_ids = nullptr; h->d_q16_sort_temp = nullptr;
-            h->q16_class_capacity = 0; h->q16_sort_temp_bytes = 0;
-            CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_cls, (size_t)n_q * 2));
-            CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_ids, (size_t)n_q * 2 * sizeof(uint32_t)));
-            CUDA_TRY(h, cudaMalloc(&h->d_q16_sort_temp, temp_bytes ? temp_bytes : 1));
-            if (!h->d_q16_hist) {
-                CUDA_TRY(h, cudaMalloc((void**)&h->d_q16_hist, 258 * sizeof(unsigned int)));
-                CUDA_TRY(h, cudaMemsetAsync(h->d_q16_hist, 0, 258 * sizeof(unsigned int), h->stream));
-            }
-            h->q16_class_capacity = n_q; h->q16_sort_temp_bytes = temp_bytes;
-        }
+    if (q16_classes_wanted(h, n_q)) {
+        { int rc_ = ensure_q16_classes(h, n_q); if (rc_) return rc_; }
         const int* stop = &h->d_state->converged;
-        const int hg = (int)std::min<long long>((n_q + 255) / 256, (long long)h->sm_count * 8);
-        k_q16_class_hist<<<hg, 256, 0, h->stream>>>(h->d_keys, bound, n_q, h->d_q16_hist, stop);
-        k_q16_class_pick<<<1, 256, 0, h->stream>>>(h->d_q16_hist, n_q, stop);
-        k_q16_class_keys<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_keys, bound, n_q, h->d_q16_hist, h->d_q16_cls,
-                                                                              h->d_q16_ids, stop);
+        if (!h->q16_hist_by_k1) {          // the seeds of this pass were not made by K1 (cold pass): histogram here
+            const int hg = (int)std::min<long long>((n_q + 255) / 256, (long long)h->sm_count * 8);
+            k_q16_class_hist<<<hg, 256, 0, h->stream>>>(h->d_keys, bound, n_q, h->d_q16_hist, h->q16_pass, stop);
+            h->launches++;
+        }
+        k_q16_class_keys<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(h->d_keys, bound, n_q, h->d_q16_hist, h->q16_pass,
+                                                                              h->d_q16_cls, h->d_q16_ids, stop);
+        size_t temp_bytes = h->q16_sort_temp_bytes;
         CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->d_q16_sort_temp, temp_bytes, (const unsigned char*)h->d_q16_cls,
                                                     h->d_q16_cls + h->q16_class_capacity, (const uint32_t*)h->d_q16_ids,
                                                     h->d_q16_ids + h->q16_class_capacity, (int)n_q, 0, Q16_CLASS_BITS, h->stream));
         perm = h->d_q16_ids + h->q16_class_capacity;
-        h->launches += 6;
+        h->launches += 4;
+        h->q16_pass++;
+        h->q16_hist_by_k1 = false;
     }
     // classes >= hard_class go to the expansion-filter kernel (flat cost per pair, no pruning to lose)
-    static const int hard_env = getenv("ICP_Q16_HARD_CLASS") ? atoi(getenv("ICP_Q16_HARD_CLASS")) : Q16_HARD_CLASS;
+    const char* hard_e = getenv("ICP_Q16_HARD_CLASS");             // tuning / tests; 16 = every class in the q16 kernel
+    const int hard_env = hard_e ? atoi(hard_e) : Q16_HARD_CLASS;
     const int hard_class = (perm != nullptr && h->prm.nn_variant != 78) ? hard_env : (1 << Q16_CLASS_BITS);
     const bool gated = perm != nullptr && hard_class < (1 << Q16_CLASS_BITS);
-    const unsigned int* first_hard = h->d_q16_hist ? h->d_q16_hist + 257 : nullptr;
-    if (gated) {
-        k_q16_class_first<<<1, 32, 0, h->stream>>>(h->d_q16_cls + h->q16_class_capacity, n_q, hard_class, h->d_q16_hist,
-                                                   &h->d_state->converged);
-        h->launches++;
-    }
     (gated ? kern_gated : kern)<<<grid, NN_THREADS, smem, h->stream>>>(
         h->d_q16_tiles, h->d_q16_etiles, h->q16_axes, h->n_tiles, tiles_per_cta, qx, qy, qz, n_q, h->d_keys, bound,
-        (uint32_t)h->base_off, &h->d_state->converged, perm, first_hard);
+        (uint32_t)h->base_off, &h->d_state->converged, perm, h->d_q16_hist, hard_class);
     h->launches++;
     if (gated) {
         auto fk = k_nn_bruteforce_filter<4, 3, true>;
@@ -1447,7 +1485,7 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
         fgy = (h->n_tiles + ftiles - 1) / ftiles;
         fk<<<dim3((unsigned)fqb, (unsigned)fgy), NN_THREADS, fsmem, h->stream>>>(
             h->d_filter_tiles, h->d_base_tiles, h->d_filter_info, h->n_tiles, ftiles, qx, qy, qz, n_q, h->d_keys,
-            (uint32_t)h->base_off, 1, &h->d_state->converged, perm, first_hard);
+            (uint32_t)h->base_off, 1, &h->d_state->converged, perm, h->d_q16_hist, hard_class);
         h->launches++;
     }
     CUDA_TRY(h, cudaGetLastError());
@@ -1456,6 +1494,7 @@ int launch_nn_q16_t(icp_handle* h, long long n_q)
 
 bool q16_variant(int v) { return v >= 50 && v <= 79; }   // 58 = 62 without the global pruning bound (A/B)
 
+bool q16_classes_wanted(const icp_handle* h, long long n_q);
 int build_tiletree(icp_handle* h);
 int ensure_tiletree_walk(icp_handle* h, long long n_q, bool fused, long long entries = 0);
 template <bool FUSED> int launch_tiletree_walk(icp_handle* h, long long n_q, int solve);
@@ -1499,7 +1538,7 @@ int launch_nn(icp_handle* h, long long n_q)
     if (q16_variant(variant)) {
         int rc = build_q16(h, (variant == 54 || variant == 55 || variant == 66) ? 1 : 0);
         if (rc) return rc;
-        if (variant != 77 && variant != 78) {       // the hard classes of the slots are served by the expansion-filter kernel
+        if (variant != 78 && q16_classes_wanted(h, n_q)) {       // the hard classes of the slots are served by the expansion-filter kernel
             rc = build_filter(h);
             if (rc) return rc;
         }
@@ -1921,12 +1960,20 @@ int enqueue_nn(icp_handle* h, long long n_q)
             h->launches += 1;
             h->pose_dirty = false;
         }
+        // a seeded pass of the q16 kernel follows: K1 accumulates the exponent histogram of its class machinery
+        const int v_ = h->prm.nn_variant;
+        h->q16_hist_by_k1 = h->bf_warm_active && n_q > 0 && h->n_tiles >= 16 && (v_ == 0 || q16_variant(v_)) && q16_classes_wanted(h, n_q);
+        if (h->q16_hist_by_k1) {
+            rc = ensure_q16_classes(h, n_q);
+            if (rc) return rc;
+        }
         if (n_q > 0)
             k_transform_queries<<<(unsigned)((n_q + 255) / 256), 256, 0, h->stream>>>(
                 h->d_state, h->d_mov, h->has_vlist ? h->d_vlist : nullptr, stride, n_q,
                 slots ? h->d_slot_pos : nullptr, qx, qy, qz, h->d_keys,
                 warm_src, h->d_base4, h->surface ? h->d_tris4 : nullptr, h->base_off,
-                h->n_local, h->bound_active ? h->d_keys : nullptr, h->bound_active ? h->d_bound : nullptr);
+                h->n_local, h->bound_active ? h->d_keys : nullptr, h->bound_active ? h->d_bound : nullptr,
+                h->q16_hist_by_k1 ? h->d_q16_hist : nullptr, h->q16_pass);
         h->launches += 1;
     }
     if (h->surface != (h->prm.nn_mode == ICP_NN_SURFACE))

@@ -261,6 +261,7 @@ k_nn_bruteforce(const float* __restrict__ base_tiles, int n_tiles, int tiles_per
 // key.  The result is bit-identical to the direct kernel (same keys, ties to the lowest index).
 // =============================================================================================
 constexpr int NNF_TILE_BYTES = NN_TILE * 4 * 4;      // x' | y' | z' | |b'|^2 planes
+__device__ __forceinline__ long long q16_first_hard(const unsigned int* __restrict__ scratch, long long n, int hard_class);
 
 struct FilterInfo {
     float cx, cy, cz;      // centre used for the primed coordinates
@@ -305,9 +306,9 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
                        const float* __restrict__ qz, long long n_queries,
                        unsigned long long* __restrict__ keys, uint32_t index_offset, int seeded,
                        const int* __restrict__ stop_flag, const uint32_t* __restrict__ perm,
-                       const unsigned int* __restrict__ first_hard)
+                       const unsigned int* __restrict__ cls_scratch, int hard_class)
 {
-    // GATED: perm = the slots in class order (see "query classes" in nn_bruteforce_q16.cuh), *first_hard = the
+    // GATED: perm = the slots in class order (see "query classes" in nn_bruteforce_q16.cuh), q16_first_hard() = the
     // first position of a HARD class.  The launch then serves only the positions from there on -- the queries
     // whose pruning radius is so large that the q16 kernel's slow path would cost more than this kernel's flat
     // 3 FFMA2 + 1 FMNMX3 per two pairs.  How many there are is only known on the device: blockIdx.x counts
@@ -316,7 +317,7 @@ k_nn_bruteforce_filter(const float* __restrict__ ftiles, const float* __restrict
     if (stop_flag != nullptr && *stop_flag != 0) return;
     long long first = 0;                      // GATED: the first position this launch serves
     if (GATED) {
-        first = (long long)*first_hard;
+        first = q16_first_hard(cls_scratch, n_queries, hard_class);
         if (first + (long long)blockIdx.x * (NN_THREADS * R) >= n_queries) return;     // blockIdx.x counts HARD blocks
     }
     extern __shared__ __align__(128) unsigned char smem_raw[];

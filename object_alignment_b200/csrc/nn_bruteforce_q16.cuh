@@ -297,74 +297,89 @@ __device__ __noinline__ unsigned long long q16_recheck(const uint32_t* tile, int
 constexpr int Q16_CLASS_BITS = 4;
 constexpr int Q16_HARD_CLASS = 3;                // classes >= this one (radius > ~11x the median's) go to the expansion-filter kernel
 
-__device__ __forceinline__ uint32_t q16_radius_exponent(const unsigned long long* __restrict__ keys,
-                                                        const float* __restrict__ bound, long long t)
+// device scratch of the class machinery (unsigned int[Q16_CLS_WORDS]): two exponent histograms used by alternate
+// passes (a pass zeroes the OTHER one for its successor), then the populations of the classes of the current pass
+constexpr int Q16_CLS_EXP = 0;                    // + 256 * (pass & 1)
+constexpr int Q16_CLS_COUNT = 512;                // [1 << Q16_CLASS_BITS]
+constexpr int Q16_CLS_WORDS = 512 + (1 << Q16_CLASS_BITS);
+
+__device__ __forceinline__ uint32_t q16_exponent_of(unsigned long long key, float bound)
 {
-    float d = key_d2(keys[t]);                       // KEY_NONE decodes as NaN bits: exponent 255, the last class
-    if (bound != nullptr) d = fminf(d, bound[t]);
+    float d = key_d2(key);                           // KEY_NONE decodes as NaN bits: exponent 255, the last class
+    d = fminf(d, bound);
     return (__float_as_uint(d) >> 23) & 0xFFu;
 }
+// Exponent histogram of the pruning radii for a pass whose seeds do not come from K1 (the cold pass: K1 adds to
+// the histogram itself otherwise).  Block 0 also zeroes the class populations of the pass.
 __global__ void k_q16_class_hist(const unsigned long long* __restrict__ keys, const float* __restrict__ bound,
-                                 long long n, unsigned int* __restrict__ hist, const int* __restrict__ stop_flag)
+                                 long long n, unsigned int* __restrict__ scratch, int pass, const int* __restrict__ stop_flag)
 {
     if (stop_flag != nullptr && *stop_flag != 0) return;
     __shared__ unsigned int sh[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < (1 << Q16_CLASS_BITS)) scratch[Q16_CLS_COUNT + threadIdx.x] = 0;
     __syncthreads();
+    const float inf = __int_as_float(0x7f800000);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
-        atomicAdd(&sh[q16_radius_exponent(keys, bound, t)], 1u);
+        atomicAdd(&sh[q16_exponent_of(keys[t], bound != nullptr ? bound[t] : inf)], 1u);
     __syncthreads();
+    unsigned int* hist = scratch + Q16_CLS_EXP + 256 * (pass & 1);
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
-// hist[256] <- the exponent bin that holds the median; the histogram itself is zeroed for the next pass
-__global__ void k_q16_class_pick(unsigned int* __restrict__ hist, long long n, const int* __restrict__ stop_flag)
+// class of every slot (relative to the exponent bin that holds the median), slot ids for the sort, and the
+// populations of the classes; block 0 zeroes the other exponent histogram for the next pass
+__global__ void __launch_bounds__(256)
+k_q16_class_keys(const unsigned long long* __restrict__ keys, const float* __restrict__ bound, long long n,
+                 unsigned int* __restrict__ scratch, int pass, unsigned char* __restrict__ cls,
+                 uint32_t* __restrict__ ids, const int* __restrict__ stop_flag)
 {
     if (stop_flag != nullptr && *stop_flag != 0) return;
-    if (threadIdx.x == 0) {
-        long long acc = 0;
-        int m = 255;
-        for (int i = 0; i < 256; ++i) {
-            acc += hist[i];
-            if (2 * acc >= n) { m = i; break; }
-        }
-        hist[256] = (unsigned int)m;
+    __shared__ unsigned int s_scan[8];
+    __shared__ int s_m;
+    __shared__ unsigned int s_cnt[1 << Q16_CLASS_BITS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int* hist = scratch + Q16_CLS_EXP + 256 * (pass & 1);
+    if (blockIdx.x == 0) scratch[Q16_CLS_EXP + 256 * ((pass + 1) & 1) + tid] = 0;
+    if (tid < (1 << Q16_CLASS_BITS)) s_cnt[tid] = 0;
+    if (tid == 0) s_m = 255;
+    // inclusive prefix sum of the 256 bins (one per thread), median bin = the first one whose prefix reaches n / 2
+    unsigned int v = hist[tid];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    if (lane == 31) s_scan[warp] = v;
+    __syncthreads();
+    unsigned int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_scan[w];
+    v += before;
+    const unsigned int below = v - hist[tid];
+    if (2ull * v >= (unsigned long long)n && 2ull * below < (unsigned long long)n) s_m = tid;     // exactly one thread (or none: n == 0)
+    __syncthreads();
+    const int m = s_m;
+    const long long t = (long long)blockIdx.x * blockDim.x + tid;
+    if (t < n) {
+        const int e = (int)q16_exponent_of(keys[t], bound != nullptr ? bound[t] : __int_as_float(0x7f800000));
+        const int c = e <= m + 2 ? 0 : min((1 << Q16_CLASS_BITS) - 1, (e - m - 1) / 2);
+        cls[t] = (unsigned char)c;
+        ids[t] = (uint32_t)t;
+        atomicAdd(&s_cnt[c], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    if (tid < (1 << Q16_CLASS_BITS) && s_cnt[tid]) atomicAdd(&scratch[Q16_CLS_COUNT + tid], s_cnt[tid]);
 }
-__global__ void k_q16_class_keys(const unsigned long long* __restrict__ keys, const float* __restrict__ bound,
-                                 long long n, const unsigned int* __restrict__ hist, unsigned char* __restrict__ cls,
-                                 uint32_t* __restrict__ ids, const int* __restrict__ stop_flag)
+// The first position (in class order) that goes to the expansion-filter launch.  Which classes do is decided from
+// the populations: when more than a tenth of the queries lie above class 0 the cloud has outliers (or overlaps the
+// base only in part) and everything above class 0 is cheaper in the flat-cost kernel (C5: 824 ms against 1093 ms
+// per pass); otherwise only classes >= hard_class go there -- the thin upper tail of an ordinary cloud is cheaper
+// in the q16 kernel (C3: 29.2 ms against 32.4 ms).
+__device__ __forceinline__ long long q16_first_hard(const unsigned int* __restrict__ scratch, long long n, int hard_class)
 {
-    if (stop_flag != nullptr && *stop_flag != 0) return;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int e = (int)q16_radius_exponent(keys, bound, t), m = (int)hist[256];
-    const int c = e <= m + 2 ? 0 : min((1 << Q16_CLASS_BITS) - 1, (e - m - 1) / 2);
-    cls[t] = (unsigned char)c;
-    ids[t] = (uint32_t)t;
-}
-// hist[257] <- the first position (in class order) that goes to the expansion-filter launch.  Which classes do is
-// decided here, from the populations: when more than a tenth of the queries lie above class 0 the cloud has
-// outliers (or overlaps the base only in part) and everything above class 0 is cheaper in the flat-cost kernel
-// (C5: 824 ms against 1093 ms per pass); otherwise only classes >= hard_class go there -- the thin upper tail of
-// an ordinary cloud is cheaper in the q16 kernel (C3: 29.2 ms against 32.4 ms).
-__global__ void k_q16_class_first(const unsigned char* __restrict__ cls_sorted, long long n, int hard_class,
-                                  unsigned int* __restrict__ hist, const int* __restrict__ stop_flag)
-{
-    if (stop_flag != nullptr && *stop_flag != 0) return;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    auto first_of = [&](int c) {
-        long long lo = 0, hi = n;
-        while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            if ((int)cls_sorted[mid] < c) lo = mid + 1; else hi = mid;
-        }
-        return lo;
-    };
-    const long long f1 = first_of(1);
-    hist[257] = (unsigned int)((n - f1) * 10 > n ? f1 : first_of(hard_class));
+    const unsigned int* cnt = scratch + Q16_CLS_COUNT;
+    const long long c0 = (long long)cnt[0];
+    if ((n - c0) * 10 > n) return c0;
+    long long f = c0;
+    for (int c = 1; c < hard_class && c < (1 << Q16_CLASS_BITS); ++c) f += (long long)cnt[c];
+    return f;
 }
 
 // grid.x = query blocks of NN_THREADS * R slots, grid.y = base ranges of tiles_per_cta tiles.
@@ -382,12 +397,12 @@ k_nn_bruteforce_q16(const uint32_t* __restrict__ qtiles, const float* __restrict
                     const float* __restrict__ qy, const float* __restrict__ qz, long long n_queries,
                     unsigned long long* __restrict__ keys, const float* __restrict__ bound,
                     uint32_t index_offset, const int* __restrict__ stop_flag, const uint32_t* __restrict__ perm,
-                    const unsigned int* __restrict__ first_hard)
+                    const unsigned int* __restrict__ cls_scratch, int hard_class)
 {
-    // GATED: *first_hard = the first position that belongs to the expansion-filter launch that follows
+    // GATED: the positions from q16_first_hard() on belong to the expansion-filter launch that follows
     // (k_nn_bruteforce_filter<.., true>: the classes with a large pruning radius); a CTA that holds only those leaves at once
     if (stop_flag != nullptr && *stop_flag != 0) return;
-    const long long n_mine = GATED ? (long long)*first_hard : n_queries;
+    const long long n_mine = GATED ? q16_first_hard(cls_scratch, n_queries, hard_class) : n_queries;
     // Positions are in class order, easy first; the query blocks are taken from the END: a block of hard
     // queries takes many times longer than an easy one, and the blocks that start last set the tail of the launch.
     const long long qblock = (perm != nullptr) ? (long long)(gridDim.x - 1 - blockIdx.x) : (long long)blockIdx.x;

@@ -493,6 +493,33 @@ def test_tree_modes_keep_slot_order_and_seeds_across_same_shape_uploads(mode):
         assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
 
 
+@pytest.mark.parametrize("hard_class", ["1", "3", "16"])
+def test_q16_class_order_and_gated_filter_on_a_small_cloud_with_outliers(monkeypatch, hard_class):
+    """The q16 kernel walks the slots in class order (similar pruning radius together) and leaves the hard classes
+    to the gated expansion-filter launch; by default only from 2^18 slots on.  Forced here on a 40k cloud with 25 %
+    far outliers (ICP_Q16_CLASS_MIN=0) for three settings of the hard class: every pass must still return the
+    oracle's keys, cold and seeded, and the percentile cut must keep the same set."""
+    monkeypatch.setenv("ICP_Q16_CLASS_MIN", "0")
+    monkeypatch.setenv("ICP_Q16_HARD_CLASS", hard_class)
+    cfg = meshgen.config_cloud(40_000, 60_000, 81, 82)
+    mov = cfg["moving"].copy()
+    rng = np.random.default_rng(83)
+    sel = rng.choice(40_000, 10_000, replace=False)
+    mov[sel] = ((rng.random((10_000, 3)) - 0.5) * 4).astype(np.float32)
+    with IcpEngine(thresh=1e9, use_target=False, reject_fraction=0.25) as e:
+        e.set_base(cfg["base"])
+        e.set_moving(mov)
+        e.set_matrices(np.eye(4), np.eye(4))
+        for it in range(4):
+            mw = e.matrix_world()
+            res = orc.make_pairs_vec(mov, np.arange(40_000), mw, np.eye(4), cfg["base"], 1e9, 1, reject_fraction=0.25,
+                                     return_all=True, nn="kdtree")
+            idx, d2 = e.nn()
+            assert np.array_equal(idx, res["idx"]) and np.array_equal(d2.view(np.uint32), res["d2"].view(np.uint32))
+            M, st = e.step()
+            assert st.pairs == int(res["keep"].sum())
+
+
 @pytest.mark.parametrize("variant", [0, 20, 2, 30, 33, 35, 36, 40, 41, 42, 44, 45, 50, 51, 52, 53, 54, 55, 56, 57,
                                      58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73, 77, 78, 79])
 def test_bruteforce_seeded_passes_stay_exact(variant):
