@@ -99,6 +99,14 @@ typedef struct icp_iter_stats {
     double  M[16];     /* the fp64 4x4 returned by affine_matrix_from_points (icp_align.py:107) */
 } icp_iter_stats;
 
+/* Environment variables read by the library (tuning and diagnostics only; results never depend on them):
+ *   ICP_Q16_CLASS_MIN   smallest number of query slots for which the brute-force pass walks the slots in
+ *                       class order and leaves the hard classes to the gated expansion-filter launch
+ *                       (default 262144; 0 = always)
+ *   ICP_Q16_HARD_CLASS  first class that goes to the gated launch when the cloud has no outliers (default 3;
+ *                       16 = every class stays in the q16 kernel)
+ *   ICP_TRACE_BUILD     when set, host wall-clock time of every one-time index build goes to stderr */
+
 typedef struct icp_handle icp_handle;
 
 int  icp_version(void);
