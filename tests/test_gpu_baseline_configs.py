@@ -163,3 +163,22 @@ def test_function_surface_rereads_coordinates_every_call():
         assert np.array_equal(i1, oi) and not np.array_equal(i0, i1)
     finally:
         nn.close()
+
+
+def test_tree_iteration_with_a_four_level_ticket_tree():
+    """1.2M query slots = 37 500 batches of 32: the ticketed reduction of the one-launch tree iteration needs FOUR
+    levels here (32^3 = 32 768 batches fill three).  K, d_stats and M of two steps against the oracle at the
+    engine's own pose, and the keys against the brute-force engine."""
+    cfg = meshgen.config_cloud(1_200_000, 200_000, 410, 411)
+    m = cfg["moving"].shape[0]
+    with IcpEngine(thresh=0.5, use_target=True, target_d=0.0, nn_mode=1) as e:
+        e.set_base(cfg["base"]); e.set_moving(cfg["moving"]); e.set_matrices(IDENT, IDENT)
+        for it in range(2):
+            mw = e.matrix_world()
+            res = _oracle_at(cfg, np.arange(m), mw)
+            idx, d2 = e.nn()
+            assert np.array_equal(idx, res["idx"]) and np.array_equal(d2.view(np.uint32), res["d2"].view(np.uint32))
+            M, st = e.step()
+            assert st.pairs == int(res["keep"].sum())
+            np.testing.assert_allclose([st.mean_dist, st.std_dist], res["d_stats"], rtol=1e-9)
+            np.testing.assert_allclose(M, orc.affine_matrix_from_points_port(res["A"], res["B"]), rtol=0, atol=1e-9)
