@@ -295,8 +295,7 @@ def build_engine(cfg, args, rank, world, local_rank, nn_mode, shard_q, dist):
     elif shard_q and world > 1:
         eng.set_base(cfg["base"])
     else:
-        # W > 1: shards that are spatially compact (Morton ranges), see IcpEngine.set_base_sharded
-        eng.set_base_sharded(cfg["base"], order=args.shard_order if world > 1 else "index")
+        eng.set_base_sharded(cfg["base"])
     upload_s = time.perf_counter() - t0
     icpdist.connect_engine(eng, dist)
     return eng, upload_s
@@ -366,27 +365,13 @@ def sharded_parity(eng, cfg, vlist, local_rank, rank, pairs_sharded, steps, args
         for _ in range(n_cmp):
             pairs_one.append(int(one.run(1)[2][0].pairs))
         pose_one = one.matrix_world()
+    same_idx = bool(np.array_equal(idx, idx1))
     same_d2 = bool(np.array_equal(d2.view(np.uint32), d21.view(np.uint32)))
-    diff = np.nonzero(idx != idx1)[0]
-    # a Morton-ordered sharding resolves exact fp32 distance ties to the lower Morton position: where the indices
-    # differ, both vertices must be at the very same S4 distance from the query (BASELINE.json: indices bit-exact
-    # when distances are non-degenerate)
-    ties = 0
-    if diff.size and diff.size <= 1000 and same_d2:
-        q = cfg["moving"][diff if vlist is None else np.asarray(vlist)[diff]].astype(np.float32)
-        def s4(b):
-            dx, dy, dz = (q[:, 0] - b[:, 0]).astype(np.float32), (q[:, 1] - b[:, 1]).astype(np.float32), (q[:, 2] - b[:, 2]).astype(np.float32)
-            t = (dx * dx).astype(np.float32)
-            t = (dy.astype(np.float64) * dy.astype(np.float64) + t.astype(np.float64)).astype(np.float32)
-            return (dz.astype(np.float64) * dz.astype(np.float64) + t.astype(np.float64)).astype(np.float32)
-        ties = int((s4(cfg["base"][idx[diff]]).view(np.uint32) == s4(cfg["base"][idx1[diff]]).view(np.uint32)).sum())
-    same_idx = bool(diff.size == 0 or ties == diff.size)
     same_k = pairs_one == [int(p) for p in pairs_sharded[:n_cmp]]
     return {"ok": bool(same_idx and same_d2 and same_k),
             "what": "rank-0 idx/d2 of all %d queries under the identity pose and pairs kept in the first %d timed "
                     "steps, sharded over %d GPUs vs the same engine unsharded on rank 0" % (idx.shape[0], n_cmp, eng.params.world_size),
-            "idx_equal": same_idx, "idx_differ_only_at_exact_distance_ties": int(diff.size), "d2_bits_equal": same_d2,
-            "pairs_per_step_equal": same_k, "shard_order": args.shard_order,
+            "idx_equal": same_idx, "d2_bits_equal": same_d2, "pairs_per_step_equal": same_k,
             "sha_sharded": digest(idx, d2), "sha_unsharded": digest(idx1, d21),
             "pairs_sharded": [int(p) for p in pairs_sharded[:n_cmp]], "pairs_unsharded": pairs_one,
             "unsharded_pose_row0": [float(x) for x in pose_one[0]]}
@@ -762,8 +747,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--nn-variant", type=int, default=0)
-    ap.add_argument("--shard-order", choices=["morton", "index"], default="morton",
-                    help="N > 1, base sharded: Morton ranges (spatially compact shards) or plain index ranges")
     ap.add_argument("--nn-mode", default="bruteforce", choices=["bruteforce", "bvh"],
                     help="bruteforce = the north-star O(M N) kernel (default, primary line); "
                          "bvh = row N2, the exact spatially-indexed search")

@@ -31,26 +31,6 @@ def stride_from_sample_fraction(sample_fraction: float) -> int:
     return round(1 / sample_fraction)
 
 
-def morton_order(xyz):
-    """Stable argsort of 30-bit Morton codes (10 bits per axis inside the bounding box of the finite points)."""
-    p = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
-    fin = np.isfinite(p).all(axis=1)
-    lo = p[fin].min(axis=0) if fin.any() else np.zeros(3)
-    hi = p[fin].max(axis=0) if fin.any() else np.ones(3)
-    ext = np.where(hi > lo, hi - lo, 1.0)
-    g = np.clip(((np.where(fin[:, None], p, lo) - lo) / ext * 1024.0).astype(np.int64), 0, 1023)
-
-    def spread(v):
-        v = (v | (v << 16)) & 0x030000FF
-        v = (v | (v << 8)) & 0x0300F00F
-        v = (v | (v << 4)) & 0x030C30C3
-        v = (v | (v << 2)) & 0x09249249
-        return v
-
-    code = spread(g[:, 0]) | (spread(g[:, 1]) << 1) | (spread(g[:, 2]) << 2)
-    return np.argsort(code, kind="stable")
-
-
 def shard_range(n_global: int, rank: int, world_size: int):
     """Contiguous equal split of the base index range [lo, hi) for `rank`."""
     lo = (n_global * rank) // world_size
@@ -156,7 +136,6 @@ class IcpEngine:
         xyz = _f32c(xyz, (-1, 3))
         n = xyz.shape[0]
         self._base_keepalive = xyz
-        self._base_perm = None
         self._check(self._lib.icp_set_base(self._h, xyz.ctypes.data, n, int(global_offset),
                                            int(n if n_global is None else n_global)))
 
@@ -173,29 +152,11 @@ class IcpEngine:
         lo, hi = shard_range(tri.shape[0], self.params.rank, self.params.world_size)
         self.set_base_triangles(tri[lo:hi], lo, tri.shape[0])
 
-    def set_base_sharded(self, xyz_full, order="index"):
-        """Upload only this rank's slice of the full base array (every rank calls it with the same array).
-
-        order="index": the contiguous index range `shard_range` gives this rank.
-        order="morton": the base is first put in Morton order (host side, once), so that a rank's shard is a
-        spatially compact part of the object: with the global pruning bound the brute-force pass then has
-        slow-path work only on the few ranks whose part of space is near a query, instead of on every rank
-        (a shard that is a random 1/W subsample of the whole surface has candidates near every query).
-        `nn()` maps the indices back to the caller's order.  Exact fp32 distance ties between two base
-        vertices then resolve to the lower MORTON position instead of the lower index (BASELINE.json exempts
-        degenerate distances from index parity)."""
+    def set_base_sharded(self, xyz_full):
+        """Upload only this rank's contiguous slice of the full base array."""
         xyz_full = np.asarray(xyz_full).reshape(-1, 3)
-        n = xyz_full.shape[0]
-        lo, hi = shard_range(n, self.params.rank, self.params.world_size)
-        if order == "index" or n == 0:
-            self.set_base(xyz_full[lo:hi], lo, n)
-            return
-        if order != "morton":
-            raise ValueError("order must be 'index' or 'morton'")
-        perm = morton_order(xyz_full)
-        shard = np.ascontiguousarray(np.asarray(xyz_full, dtype=np.float32)[perm[lo:hi]])
-        self.set_base(shard, lo, n)
-        self._base_perm = perm
+        lo, hi = shard_range(xyz_full.shape[0], self.params.rank, self.params.world_size)
+        self.set_base(xyz_full[lo:hi], lo, xyz_full.shape[0])
 
     def set_moving(self, xyz, vlist=None):
         xyz = _f32c(xyz, (-1, 3))
@@ -258,9 +219,6 @@ class IcpEngine:
         idx = np.empty(n, dtype=np.int32)
         d2 = np.empty(n, dtype=np.float32)
         self._check(self._lib.icp_nn(self._h, idx.ctypes.data, d2.ctypes.data))
-        perm = getattr(self, "_base_perm", None)
-        if perm is not None:                         # set_base_sharded(order="morton"): back to the caller's indices
-            idx = np.where(idx >= 0, perm[np.maximum(idx, 0)], -1).astype(np.int32)
         return idx, d2
 
     def make_pairs(self, calc_stats=False):

@@ -30,7 +30,7 @@ if shard == 1:
     icpdist.connect_engine(eng, dist)
     eng.set_moving_sharded(cfg["moving"])
 else:
-    eng.set_base_sharded(cfg["base"], order=os.environ.get("ICP_SHARD_ORDER", "index"))
+    eng.set_base_sharded(cfg["base"])
     icpdist.connect_engine(eng, dist)
     if os.environ.get("ICP_COLLECTIVE") == "1" and world > 1:
         eng.set_moving_collective(cfg["moving"])  # 1/world of the coordinates per host link + ncclAllGather
@@ -120,9 +120,8 @@ def test_function_surface_shards_by_search_kind(tmp_path, nn_mode):
 
 
 @pytest.mark.parametrize("rf,nn_mode,shard,collective", [(0.0, 0, 0, 0), (0.2, 0, 0, 0), (0.0, 0, 0, 1), (0.0, 1, 0, 0),
-                                                         (0.2, 1, 0, 0), (0.0, 1, 1, 0), (0.0, 0, 0, 2), (0.2, 0, 0, 2)])
+                                                         (0.2, 1, 0, 0), (0.0, 1, 1, 0)])
 def test_sharded_base_matches_single_gpu(tmp_path, rf, nn_mode, shard, collective):
-    # collective == 2: the base is sharded in Morton order (spatially compact shards), plain upload of the moving set
     n = _gpu_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -133,8 +132,7 @@ def test_sharded_base_matches_single_gpu(tmp_path, rf, nn_mode, shard, collectiv
     for w in (1, world):
         out = tmp_path / ("out%d.npz" % w)
         env = dict(os.environ, ICP_OUT=str(out), ICP_RF=str(rf), ICP_NN_MODE=str(nn_mode),
-                   ICP_SHARD=str(shard if w > 1 else 0), ICP_COLLECTIVE=str(collective),
-                   ICP_SHARD_ORDER="morton" if (collective == 2 and w > 1) else "index")
+                   ICP_SHARD=str(shard if w > 1 else 0), ICP_COLLECTIVE=str(collective))
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(w),
                "--master-addr", "127.0.0.1", "--master-port", str(29600 + w), str(script)]
         subprocess.run(cmd, check=True, env=env, timeout=600, cwd=ROOT)

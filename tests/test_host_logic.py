@@ -53,26 +53,3 @@ def test_meshgen_configs():
     c = meshgen.config_cloud(1000, 2000, 1, 2)
     assert c["base"].shape == (2000, 3) and c["moving"].shape == (1000, 3)
     assert np.array_equal(c["base"], meshgen.config_cloud(1000, 2000, 1, 2)["base"])
-
-
-def test_morton_order_is_a_stable_permutation_that_groups_space():
-    """set_base_sharded(order="morton"): a permutation of all vertices (non-finite ones included), equal
-    codes keep their index order, and a contiguous range of it is spatially compact (so that a rank's
-    shard is a part of the object, not a subsample of all of it)."""
-    from object_alignment_b200.engine import morton_order, shard_range
-    rng = np.random.default_rng(5)
-    pts = rng.random((20_000, 3)).astype(np.float32)
-    pts[7] = np.nan
-    pts[11] = pts[3]                                   # duplicate: same code, index order kept
-    perm = morton_order(pts)
-    assert np.array_equal(np.sort(perm), np.arange(20_000))
-    pos = np.empty(20_000, np.int64); pos[perm] = np.arange(20_000)
-    assert pos[3] < pos[11]
-    vol_index, vol_morton = [], []
-    ok = np.isfinite(pts).all(axis=1)
-    for r in range(8):
-        lo, hi = shard_range(20_000, r, 8)
-        a = pts[lo:hi][ok[lo:hi]]; b = pts[perm[lo:hi]][ok[perm[lo:hi]]]
-        vol_index.append(np.prod(a.std(0))); vol_morton.append(np.prod(b.std(0)))       # spread of the bulk (a range may straddle two octants)
-    assert np.mean(vol_morton) < 0.3 * np.mean(vol_index)
-    assert morton_order(np.zeros((0, 3), np.float32)).shape == (0,)
