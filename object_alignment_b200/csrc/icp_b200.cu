@@ -4,16 +4,20 @@
 // OBJECT_OT_icp_align.execute, reference operators/icp_align.py:96-151) is this launch train,
 // with nothing crossing PCIe and no host synchronisation in between:
 //
-//   k_prepare_pose       imx1 = inv(mw_align), imx2 = inv(mw_base)              general.py:262-266
-//   k_transform_queries  q = imx2 @ (mx1 @ v.co) for the sampled vlist          general.py:274-275,287
-//   k_nn_bruteforce      nearest base vertex per query -> uint64 keys           general.py:297 (D2)
+//   brute force (nn_mode ICP_NN_BRUTEFORCE, the north-star path; base sharded across ranks)
+//   k_prepare_pose       imx1 = inv(mw_align), imx2 = inv(mw_base) (only after icp_set_matrices) general.py:262-266
+//   k_transform_queries  q = imx2 @ (mx1 @ v.co) for the sampled vlist, seeds, global bound       general.py:274-275,287
+//   [k_q16_class_keys + 4-bit radix sort: the slots in class order, from 2^18 slots on]          nn_bruteforce_q16.cuh
+//   k_nn_bruteforce_q16  nearest base vertex per query -> uint64 keys                            general.py:297 (D2)
+//   [k_nn_bruteforce_filter<GATED>: the hard classes (outliers)]
 //   [ncclAllReduce MIN over the keys when the base is sharded across ranks]
-//   [radix select of the reject_fraction percentile when enabled]               NEW
-//   k_filter_moments     world distance, thresh, targets, fp64 moment partials  general.py:299-328,160-181
-//   k_reduce_moments     fixed-order sum of the partials
-//   [ncclAllReduce SUM over 20 doubles when sharded]
-//   k_solve_update       Jacobi SVD -> R, scale, t -> M; matrix_world @= fp32(M); convergence ring
-//                                                   general.py:181-217, icp_align.py:116-149
+//   [radix select of the reject_fraction percentile when enabled]                                NEW
+//   k_filter_moments     world distance, thresh, targets, fp64 moment partials                   general.py:299-328,160-181
+//   k_reduce_solve       fixed-order sum of the partials, Jacobi SVD -> R, scale, t -> M; matrix_world @= fp32(M);
+//                        convergence ring  (multi-GPU: k_reduce_moments, ncclAllReduce SUM over 20 doubles, k_solve_update)
+//                                                                                                general.py:181-217, icp_align.py:116-149
+//   tree / surface search (ICP_NN_BVH, ICP_NN_SURFACE; queries sharded across ranks)
+//   k_nn_tiletree_p<FUSED> / k_nn_surface_defer<FUSED, TICKET>: ALL of the above in one launch (nn_tiletree.cuh)
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>

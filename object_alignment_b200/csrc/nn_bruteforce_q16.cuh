@@ -1,5 +1,5 @@
 // nn_bruteforce_q16.cuh -- K2, fifth form: brute-force nearest vertex whose hot loop is ONE integer
-// instruction per two (query, base vertex) pairs (nn_variant 50..57; the default for seeded passes).
+// instruction per two (query, base vertex) pairs (nn_variant 50..79; variant 71 is the default for seeded passes).
 //
 // Replaces the per-vertex `base_bvh.find_nearest(co_find)` of the reference
 // (functions/general.py:297, nearest-VERTEX variant).  Still O(M N): every pair is

@@ -1,5 +1,5 @@
 // nn_bruteforce_slab.cuh -- K2, fourth form: brute-force nearest vertex with a 1-FMA "slab" filter in
-// front of the cylinder filter of nn_bruteforce_cyl.cuh (nn_variant 40..45; the default for seeded passes).
+// front of the cylinder filter of nn_bruteforce_cyl.cuh (nn_variant 40..45; the round-1 default for seeded passes, superseded by nn_bruteforce_q16.cuh).
 //
 // Replaces the per-vertex `base_bvh.find_nearest(co_find)` of the reference
 // (functions/general.py:297, nearest-VERTEX variant).  Still O(M N): every
