@@ -200,7 +200,7 @@ __global__ void k_query_codes(const float* __restrict__ mov, const int* __restri
         t = fminf(fmaxf(t, 0.0f), 1.0f);
         g[k] = (uint32_t)fminf(t * 2097152.0f, 2097151.0f);
     }
-    codes[p] = morton_expand21(g[0]) | (morton_expand21(g[1]) << 1) | (morton_expand21(g[2]) << 2);
+    codes[p] = curve_code21(g[0], g[1], g[2]);
     pos[p] = (uint32_t)p;
 }
 __global__ void k_gather_mov_slots(const float* __restrict__ mov, const int* __restrict__ vlist, int stride,

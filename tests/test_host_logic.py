@@ -53,3 +53,45 @@ def test_meshgen_configs():
     c = meshgen.config_cloud(1000, 2000, 1, 2)
     assert c["base"].shape == (2000, 3) and c["moving"].shape == (1000, 3)
     assert np.array_equal(c["base"], meshgen.config_cloud(1000, 2000, 1, 2)["base"])
+
+
+def test_hilbert_curve_code_restated_is_a_bijection_with_unit_steps():
+    """`curve_code21` (csrc/nn_bvh.cuh: Skilling's transpose algorithm, the order of base vertices, triangles and
+    query slots), restated with 4 bits per axis: every cell gets its own position and consecutive positions are
+    adjacent cells -- the property the warp patches and the leaf tiles rely on for tight boxes (any order would
+    be CORRECT; this one has no jumps)."""
+    bits = 4
+
+    def code(gx, gy, gz):
+        x = [gx, gy, gz]
+        q = 1 << (bits - 1)
+        while q > 1:
+            p = q - 1
+            for i in range(3):
+                if x[i] & q:
+                    x[0] ^= p
+                else:
+                    t = (x[0] ^ x[i]) & p
+                    x[0] ^= t
+                    x[i] ^= t
+            q >>= 1
+        x[1] ^= x[0]
+        x[2] ^= x[1]
+        t, q = 0, 1 << (bits - 1)
+        while q > 1:
+            if x[2] & q:
+                t ^= q - 1
+            q >>= 1
+        x = [v ^ t for v in x]
+        c = 0
+        for b in range(bits - 1, -1, -1):
+            for i in range(3):
+                c = (c << 1) | ((x[i] >> b) & 1)
+        return c
+
+    n = 1 << bits
+    cells = np.array([(a, b, c) for a in range(n) for b in range(n) for c in range(n)])
+    codes = np.array([code(*map(int, cell)) for cell in cells])
+    assert np.array_equal(np.sort(codes), np.arange(n ** 3))
+    walk = cells[np.argsort(codes)]
+    assert (np.abs(np.diff(walk, axis=0)).sum(axis=1) == 1).all()
