@@ -41,7 +41,7 @@ typedef enum icp_status {
 
 typedef enum icp_nn_mode {
     ICP_NN_BRUTEFORCE = 0, /* O(M N) tiled min-search, the north-star path (general.py:297, D2) */
-    ICP_NN_BVH = 1         /* exact search through an implicit BVH over Morton-sorted base vertices
+    ICP_NN_BVH = 1         /* exact search through an implicit BVH over base vertices sorted along a space-filling curve
                               (the "KD-tree equivalent"); bit-identical results */
     , ICP_NN_SURFACE = 2   /* closest point on the TRIANGULATED SURFACE of the base mesh -- the reference's
                               real BVHTree.find_nearest semantics; needs
@@ -80,7 +80,7 @@ typedef struct icp_params {
                                 with every class in the q16 kernel, 58 = without the global pruning bound, 79 = greedy
                                 tile-tree seeds for the cold pass instead of the exact tree search, 59 =
                                 cold pass by the expansion filter instead of tile-tree seeds).
-                                Tree (ICP_NN_BVH): default = persistent warp walk over a 32-ary tree of Morton
+                                Tree (ICP_NN_BVH): default = persistent warp walk over a 32-ary tree of Hilbert-ordered
                                 tiles, the whole iteration in one launch; 13 = its first generation (one CTA per
                                 128 slots), 12 = binary LBVH packet walk, 10 per-thread walk, 11 packet walk
                                 without the fused epilogue.  Surface: 10 per-thread walk, 11 packet walk with
