@@ -1359,7 +1359,10 @@ int build_q16(icp_handle* h, int want_order)
         { int rc = ensure(h, h->d_q16_etiles, h->q16_etiles_cap, (long long)h->n_tiles * CYL_TILE_FLOATS); if (rc) return rc; }
         k_bbox_partial<<<pb, 256, 0, h->stream>>>(h->d_base4, n, part);
         k_bbox_final<<<1, 192, 0, h->stream>>>(part, pb, bbox);
-        k_morton_codes<<<gn, 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order);
+        // the 1024-vertex tiles of the brute-force kernels follow the MORTON curve: its ranges of 2^10 positions are
+        // axis-aligned cells, whose boxes the slab and cull tests prune best (ICP_Q16_TILE_CURVE=hilbert for the A/B)
+        static const bool q16_hilbert = getenv("ICP_Q16_TILE_CURVE") && !strcmp(getenv("ICP_Q16_TILE_CURVE"), "hilbert");
+        k_morton_codes<<<gn, 256, 0, h->stream>>>(h->d_base4, n, bbox, codes, order, q16_hilbert ? 0 : 1);
         CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, codes, codes_out, order, order_out, (int)n, 0, 63, h->stream));
         // a, b = the two longest axes of the shard (the candidate slab axes), c = the shortest
         float hb[6];

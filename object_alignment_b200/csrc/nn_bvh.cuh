@@ -89,14 +89,16 @@ __global__ void k_bbox_final(const float* __restrict__ part, int n_part, float* 
 // Position of a grid cell (21 bits per axis) along the space-filling curve that orders base vertices, triangles
 // and query slots.  Default: the HILBERT curve (Skilling's transpose algorithm) -- consecutive positions are
 // always adjacent cells, so 32 consecutive slots (a warp's patch) or 32 / 1024 consecutive vertices (a tile) never
-// straddle one of the Morton curve's jumps across the object.  Any order is valid (the searches are exact
+// straddle one of the Morton curve's jumps across the object (the brute-force kernels' 1024-vertex tiles keep the Morton order: `morton` argument).  Any order is valid (the searches are exact
 // whatever the order); -DICP_CURVE_MORTON keeps the plain bit interleave for A/B runs.  Both are radix-tree
 // friendly: a common prefix of the code is a sub-cube.
-__device__ __forceinline__ uint64_t curve_code21(uint32_t gx, uint32_t gy, uint32_t gz)
+__device__ __forceinline__ uint64_t curve_code21(uint32_t gx, uint32_t gy, uint32_t gz, bool morton = false)
 {
 #ifdef ICP_CURVE_MORTON
-    return morton_expand21(gx) | (morton_expand21(gy) << 1) | (morton_expand21(gz) << 2);
-#else
+    morton = true;
+#endif
+    if (morton) return morton_expand21(gx) | (morton_expand21(gy) << 1) | (morton_expand21(gz) << 2);
+    {
     uint32_t X[3] = {gx, gy, gz};
     for (uint32_t Q = 1u << 20; Q > 1u; Q >>= 1) {          // undo the excess work of the Gray-code walk
         const uint32_t P = Q - 1u;
@@ -111,11 +113,11 @@ __device__ __forceinline__ uint64_t curve_code21(uint32_t gx, uint32_t gy, uint3
     for (uint32_t Q = 1u << 20; Q > 1u; Q >>= 1) if (X[2] & Q) t ^= Q - 1u;
     X[0] ^= t; X[1] ^= t; X[2] ^= t;
     return (morton_expand21(X[0]) << 2) | (morton_expand21(X[1]) << 1) | morton_expand21(X[2]);
-#endif
+    }
 }
 
 __global__ void k_morton_codes(const float4* __restrict__ pts, long long n, const float* __restrict__ bbox,
-                               unsigned long long* __restrict__ codes, uint32_t* __restrict__ order)
+                               unsigned long long* __restrict__ codes, uint32_t* __restrict__ order, int morton = 0)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -129,7 +131,7 @@ __global__ void k_morton_codes(const float4* __restrict__ pts, long long n, cons
         t = fminf(fmaxf(t, 0.0f), 1.0f);
         g[k] = (uint32_t)fminf(t * 2097152.0f, 2097151.0f);
     }
-    codes[i] = curve_code21(g[0], g[1], g[2]);
+    codes[i] = curve_code21(g[0], g[1], g[2], morton != 0);
     order[i] = (uint32_t)i;
 }
 
