@@ -273,3 +273,44 @@ def test_global_pruning_bound_is_valid():
         assert (d_new_same_vertex <= bound).all()
         d_new_all = s4_d2(np.broadcast_to(q_new[:, None, :], (3000, 4000, 3)), np.broadcast_to(base[None], (3000, 4000, 3)))
         assert (d_new_all.min(axis=1) <= bound).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# q16 query classes (csrc/nn_bruteforce_q16.cuh: k_q16_class_keys, q16_first_hard), restated: the class of a
+# slot from the exponent of its squared pruning radius relative to the bin of the median, and the rule that
+# decides which classes the gated expansion-filter launch serves.  (Performance logic only: every setting
+# returns the same keys -- that is what test_q16_class_order_and_gated_filter_on_a_small_cloud_with_outliers
+# checks on the GPU.)
+# ------------------------------------------------------------------------------------------------
+def q16_classes(d2):
+    e = ((np.asarray(d2, F).view(np.uint32) >> 23) & 0xFF).astype(np.int64)
+    hist = np.bincount(e, minlength=256)
+    csum = np.cumsum(hist)
+    m = int(np.argmax(2 * csum >= e.size))                     # the first bin whose prefix reaches n / 2
+    cls = np.where(e <= m + 2, 0, np.minimum(15, (e - m - 1) // 2))
+    return cls, m
+
+
+def q16_first_hard(cls, hard_class=3):
+    n, cnt = cls.size, np.bincount(cls, minlength=16)
+    if (n - cnt[0]) * 10 > n:
+        return int(cnt[0])
+    return int(cnt[:hard_class].sum())
+
+
+def test_q16_classes_are_monotone_and_the_gate_follows_the_populations():
+    rng = np.random.default_rng(41)
+    inl = (rng.random(100_000) * 4e-6 + 1e-7).astype(F)         # squared radii of an aligned cloud
+    cls, m = q16_classes(inl)
+    order = np.argsort(inl, kind="stable")
+    assert (np.diff(cls[order]) >= 0).all()                     # a larger radius never gets a lower class
+    assert (cls == 0).mean() > 0.95 and cls.max() <= 2
+    assert q16_first_hard(cls) == inl.size                      # nothing for the gated launch: classes < 3 stay in q16
+    out = np.concatenate([inl[:75_000], (rng.random(25_000) * 0.5 + 0.01).astype(F)])   # 25 % far outliers
+    cls, _ = q16_classes(out)
+    assert (cls[:75_000] <= 1).all() and (cls[75_000:] >= 4).all()
+    assert q16_first_hard(cls) == int((cls == 0).sum())         # a cloud with outliers: everything above class 0 is gated
+    tail = np.concatenate([inl[:99_000], (rng.random(1_000) * 0.5 + 0.01).astype(F)])   # a thin far tail (1 %)
+    cls, _ = q16_classes(tail)
+    assert q16_first_hard(cls) == int((cls < 3).sum()) == 99_000
+    assert q16_first_hard(cls, hard_class=16) == tail.size      # ICP_Q16_HARD_CLASS=16: the gate is off
